@@ -1,0 +1,659 @@
+// C-ABI entry points (include/catfish_b200.h): model construction, ragged-batch planning and
+// the kernel sequence of one inference call.  No CPU fallback: every entry that computes
+// requires a CUDA device and fails with CF_ERR_NO_DEVICE / CF_ERR_CUDA otherwise.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "model.cuh"
+
+namespace cf {
+
+// ---------------------------------------------------------------- errors / counters
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+int DevBuf::ensure(size_t want) {
+    if (want <= bytes) return CF_OK;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    const size_t grow = want + want / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, grow);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        set_error("cudaMalloc of %zu bytes failed: %s", grow, cudaGetErrorString(e));
+        cudaGetLastError();
+        return CF_ERR_ALLOC;
+    }
+    bytes = grow;
+    return CF_OK;
+}
+void DevBuf::release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+
+int HostBuf::ensure(size_t want) {
+    if (want <= bytes) return CF_OK;
+    if (ptr) { cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
+    const size_t grow = want + want / 8 + 256;
+    cudaError_t e = cudaMallocHost(&ptr, grow);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        set_error("cudaMallocHost of %zu bytes failed: %s", grow, cudaGetErrorString(e));
+        cudaGetLastError();
+        return CF_ERR_ALLOC;
+    }
+    bytes = grow;
+    return CF_OK;
+}
+void HostBuf::release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
+
+// ---------------------------------------------------------------- weights
+static int check_desc(const cf_model_desc& d) {
+    if (d.network_type < CF_NET_RESNET_RNN || d.network_type > CF_NET_RESNET) {
+        set_error("unknown network_type %d", d.network_type);
+        return CF_ERR_BAD_ARG;
+    }
+    if (d.window != kWindow) {
+        set_error("window must be 35 (rnn_class.py:27), got %d", d.window);
+        return CF_ERR_BAD_ARG;
+    }
+    const bool res = d.network_type != CF_NET_RNN, rnn = d.network_type != CF_NET_RESNET;
+    if (res && (d.layer_size_res < 1 || d.layer_size_res > 1024 || d.n_layers_res < 1 || d.n_layers_res > 64)) {
+        set_error("bad residual hyper-parameters (layer_size_res %d, n_layers_res %d)", d.layer_size_res, d.n_layers_res);
+        return CF_ERR_BAD_ARG;
+    }
+    if (rnn && (d.layer_size < 1 || d.layer_size > 256 || d.n_layers < 1 || d.n_layers > 64)) {
+        set_error("bad GRU hyper-parameters (layer_size %d in 1..256, n_layers %d)", d.layer_size, d.n_layers);
+        return CF_ERR_BAD_ARG;
+    }
+    if (d.engine < CF_ENGINE_AUTO || d.engine > CF_ENGINE_SIMT) {
+        set_error("unknown engine %d", d.engine);
+        return CF_ERR_BAD_ARG;
+    }
+    return CF_OK;
+}
+
+int expected_tensor_shapes(const cf_model_desc& d, std::vector<std::vector<int64_t>>* shapes) {
+    CF_TRY(check_desc(d));
+    shapes->clear();
+    int64_t feat = 1;
+    if (d.network_type != CF_NET_RNN) {
+        const int64_t c = d.layer_size_res;
+        for (int b = 0; b < d.n_layers_res; ++b) {
+            const int64_t cin = b == 0 ? 1 : c;
+            const int64_t ks[4] = {1, 1, 3, 1};
+            const int64_t ci[4] = {cin, cin, c, c};
+            for (int j = 0; j < 4; ++j) {
+                shapes->push_back({ks[j], ci[j], c});
+                for (int v = 0; v < 5; ++v) shapes->push_back({c});   // bias, gamma, beta, mean, var
+            }
+        }
+        feat = c;
+    }
+    if (d.network_type != CF_NET_RESNET) {
+        const int64_t h = d.layer_size;
+        for (int l = 0; l < d.n_layers; ++l) {
+            const int64_t fin = l == 0 ? feat : 2 * h;
+            for (int dir = 0; dir < 2; ++dir) {
+                shapes->push_back({fin + h, 2 * h});
+                shapes->push_back({2 * h});
+                shapes->push_back({fin + h, h});
+                shapes->push_back({h});
+            }
+        }
+        feat = 2 * h;
+    }
+    shapes->push_back({feat, 1});
+    shapes->push_back({1});
+    return CF_OK;
+}
+
+int build_host_model(const cf_model_desc& d, const float* const* t, HostModel* out) {
+    out->desc = d;
+    int idx = 0;
+    int feat = 1;
+    if (d.network_type != CF_NET_RNN) {
+        const int c = d.layer_size_res;
+        for (int b = 0; b < d.n_layers_res; ++b) {
+            const int cin = b == 0 ? 1 : c;
+            const int ks[4] = {1, 1, 3, 1};
+            const int ci[4] = {cin, cin, c, c};
+            for (int j = 0; j < 4; ++j) {
+                const float* kern = t[idx++];
+                const float* bias = t[idx++];
+                const float* gamma = t[idx++];
+                const float* beta = t[idx++];
+                const float* mean = t[idx++];
+                const float* var = t[idx++];
+                ConvLayer cl;
+                cl.k = ks[j]; cl.cin = ci[j]; cl.cout = c;
+                cl.w.resize((size_t)cl.k * cl.cin * c);
+                cl.b.resize(c);
+                for (int co = 0; co < c; ++co) {
+                    // fold in double, store float (batch_normalization with moving statistics)
+                    const double s = (double)gamma[co] / std::sqrt((double)var[co] + (double)d.bn_epsilon);
+                    cl.b[co] = (float)((double)bias[co] * s + ((double)beta[co] - (double)mean[co] * s));
+                    for (int q = 0; q < cl.k * cl.cin; ++q)
+                        cl.w[(size_t)q * c + co] = (float)((double)kern[(size_t)q * c + co] * s);
+                }
+                out->convs.push_back(std::move(cl));
+            }
+        }
+        feat = c;
+    }
+    if (d.network_type != CF_NET_RESNET) {
+        const int h = d.layer_size;
+        for (int l = 0; l < d.n_layers; ++l) {
+            const int fin = l == 0 ? feat : 2 * h;
+            for (int dir = 0; dir < 2; ++dir) {
+                const float* wg = t[idx++];   // [fin+h][2h]
+                const float* bg = t[idx++];   // [2h]
+                const float* wc = t[idx++];   // [fin+h][h]
+                const float* bc = t[idx++];   // [h]
+                GruDir g;
+                g.in = fin; g.h = h;
+                g.wx.resize((size_t)fin * 3 * h);
+                g.bx.resize(3 * h);
+                g.wgh.resize((size_t)h * 2 * h);
+                g.wch.resize((size_t)h * h);
+                for (int k = 0; k < fin; ++k) {
+                    for (int j = 0; j < 2 * h; ++j) g.wx[(size_t)k * 3 * h + j] = wg[(size_t)k * 2 * h + j];
+                    for (int j = 0; j < h; ++j) g.wx[(size_t)k * 3 * h + 2 * h + j] = wc[(size_t)k * h + j];
+                }
+                for (int j = 0; j < 2 * h; ++j) g.bx[j] = bg[j];
+                for (int j = 0; j < h; ++j) g.bx[2 * h + j] = bc[j];
+                for (int k = 0; k < h; ++k) {
+                    for (int j = 0; j < 2 * h; ++j) g.wgh[(size_t)k * 2 * h + j] = wg[(size_t)(fin + k) * 2 * h + j];
+                    for (int j = 0; j < h; ++j) g.wch[(size_t)k * h + j] = wc[(size_t)(fin + k) * h + j];
+                }
+                out->gru.push_back(std::move(g));
+            }
+        }
+        feat = 2 * h;
+    }
+    const float* hw = t[idx++];
+    const float* hb = t[idx++];
+    out->head_w.assign(hw, hw + feat);
+    out->head_b = hb[0];
+    return CF_OK;
+}
+
+// dense window table for cf_infer_windows: window g covers x[35 g .. 35 g + 35)
+__global__ void dense_window_table_kernel(int64_t n_windows, int64_t n_slots, int64_t* __restrict__ src,
+                                          int32_t* __restrict__ valid, int32_t* __restrict__ read) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_slots) return;
+    const bool real = g < n_windows;
+    src[g] = real ? g * kWindow : -1;
+    valid[g] = real ? kWindow : 0;
+    read[g] = -1;
+}
+
+}  // namespace cf
+
+// ---------------------------------------------------------------- handle
+struct cf_model {
+    cf::HostModel hm;
+    int device = 0;
+    int engine = CF_ENGINE_SIMT;
+    cf::SimtEngine* simt = nullptr;
+    cf::TcEngine* tc = nullptr;
+    // per-batch scratch
+    cf::HostBuf pin_plan;            // offsets + win_off staging
+    cudaEvent_t plan_copied = nullptr;
+    cf::DevBuf plan_dev;             // offsets[R+1] | win_off[R+1]
+    cf::DevBuf stats, wide_flags, wide_scratch;
+    cf::DevBuf tab_src, tab_valid, tab_read;
+    cf::DevBuf probs_internal;
+    cf::IntervalScratch k6;
+    // host-buffer entry point
+    cf::DevBuf h_raw, h_intervals, h_ioff, h_probs;
+    cf::HostBuf pin_io;
+    std::mutex mu;
+};
+
+namespace cf {
+
+constexpr int kWideSlots = 64;
+
+static int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); catfish_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return CF_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (0..%d)", device, n - 1);
+        return CF_ERR_BAD_ARG;
+    }
+    CF_CUDA(cudaSetDevice(device));
+    return CF_OK;
+}
+
+static int engine_forward(cf_model* m, const int16_t* raw, const double* stats, const float* xwin,
+                          WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream) {
+    if (m->engine == CF_ENGINE_TCGEN05)
+        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream);
+    return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream);
+}
+
+// Validate offsets and lay out the windows of every read (infer.py:32-43).
+static int make_plan(const int64_t* offsets, int32_t n_reads, BatchPlan* p) {
+    p->n_reads = n_reads;
+    p->win_off.assign((size_t)n_reads + 1, 0);
+    int64_t w = 0;
+    for (int32_t r = 0; r < n_reads; ++r) {
+        const int64_t len = offsets[r + 1] - offsets[r];
+        if (len < 0 || offsets[r] < 0) {
+            set_error("offsets must be non-negative and non-decreasing (read %d)", r);
+            return CF_ERR_BAD_ARG;
+        }
+        if (len == 0) {
+            set_error("read %d is empty: the reference raises IndexError (infer.py:151,184)", r);
+            return CF_ERR_EMPTY_READ;
+        }
+        if (len >= (int64_t)1 << 31) {
+            set_error("read %d has %lld samples; reads must be shorter than 2^31", r, (long long)len);
+            return CF_ERR_BAD_ARG;
+        }
+        p->win_off[r] = w;
+        w += len / kWindow + 1;          // padding 35 - L % 35, a whole window when 35 | L
+    }
+    p->win_off[n_reads] = w;
+    p->total_windows = w;
+    p->total_samples = n_reads > 0 ? offsets[n_reads] - offsets[0] : 0;
+    p->n_tiles = ceil_div(w, kTileWindows);
+    return CF_OK;
+}
+
+// Copy offsets (rebased to 0) and win_off to the device through the pinned staging buffer.
+static int upload_plan(cf_model* m, const int64_t* offsets, const BatchPlan& p, cudaStream_t stream,
+                       const int64_t** offsets_dev, const int64_t** win_off_dev) {
+    const size_t n = (size_t)p.n_reads + 1;
+    if (m->plan_copied) CF_CUDA(cudaEventSynchronize(m->plan_copied));   // staging still in flight?
+    CF_TRY(m->pin_plan.ensure(2 * n * sizeof(int64_t)));
+    CF_TRY(m->plan_dev.ensure(2 * n * sizeof(int64_t)));
+    int64_t* st = m->pin_plan.as<int64_t>();
+    for (size_t i = 0; i < n; ++i) st[i] = offsets[i] - offsets[0];
+    memcpy(st + n, p.win_off.data(), n * sizeof(int64_t));
+    CF_CUDA(cudaMemcpyAsync(m->plan_dev.ptr, st, 2 * n * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    if (!m->plan_copied) CF_CUDA(cudaEventCreateWithFlags(&m->plan_copied, cudaEventDisableTiming));
+    CF_CUDA(cudaEventRecord(m->plan_copied, stream));
+    *offsets_dev = m->plan_dev.as<int64_t>();
+    *win_off_dev = m->plan_dev.as<int64_t>() + n;
+    return CF_OK;
+}
+
+static int ensure_table(cf_model* m, int64_t n_tiles, WindowTable* tab) {
+    const size_t slots = (size_t)n_tiles * kTileWindows;
+    CF_TRY(m->tab_src.ensure(slots * sizeof(int64_t)));
+    CF_TRY(m->tab_valid.ensure(slots * sizeof(int32_t)));
+    CF_TRY(m->tab_read.ensure(slots * sizeof(int32_t)));
+    tab->src = m->tab_src.as<int64_t>();
+    tab->valid = m->tab_valid.as<int32_t>();
+    tab->read = m->tab_read.as<int32_t>();
+    return CF_OK;
+}
+
+static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t* offsets_host,
+                              int32_t n_reads, float* probs_dev, int64_t* intervals_dev,
+                              int64_t* interval_offsets_dev, int64_t capacity, double threshold,
+                              int32_t min_run, int32_t ext_left, int32_t ext_right,
+                              cudaStream_t stream) {
+    BatchPlan plan;
+    CF_TRY(make_plan(offsets_host, n_reads, &plan));
+    if (n_reads == 0) {
+        CF_CUDA(cudaMemsetAsync(interval_offsets_dev, 0, sizeof(int64_t), stream));
+        return CF_OK;
+    }
+    const int16_t* raw0 = raw_dev + offsets_host[0];
+    const int64_t *offsets_dev, *win_off_dev;
+    CF_TRY(upload_plan(m, offsets_host, plan, stream, &offsets_dev, &win_off_dev));
+    CF_TRY(m->stats.ensure(sizeof(double) * 2 * (size_t)n_reads));
+    CF_TRY(m->wide_flags.ensure(sizeof(int32_t) * (size_t)n_reads));
+    CF_TRY(m->wide_scratch.ensure(k1_wide_scratch_bytes(kWideSlots)));
+    WindowTable tab;
+    CF_TRY(ensure_table(m, plan.n_tiles, &tab));
+    float* probs = probs_dev;
+    if (!probs) {
+        CF_TRY(m->probs_internal.ensure(sizeof(float) * (size_t)plan.total_samples));
+        probs = m->probs_internal.as<float>();
+    }
+    CF_TRY(k1_read_stats(raw0, offsets_dev, n_reads, m->stats.as<double>(), m->wide_flags.as<int32_t>(),
+                         m->wide_scratch.as<uint32_t>(), kWideSlots, stream));
+    CF_TRY(k1_window_table(offsets_dev, win_off_dev, n_reads, plan.total_windows, plan.n_tiles, tab, stream));
+    CF_TRY(engine_forward(m, raw0, m->stats.as<double>(), nullptr, tab, plan.n_tiles, probs, stream));
+    CF_TRY(k6_call_intervals(m->k6, probs, BITS_FROM_F32, threshold, 1, offsets_dev, n_reads,
+                             plan.total_samples, intervals_dev, interval_offsets_dev, nullptr, capacity,
+                             min_run, ext_left, ext_right, stream));
+    return CF_OK;
+}
+
+}  // namespace cf
+
+// ================================================================== extern "C"
+extern "C" {
+
+int cf_abi_version(void) { return CF_ABI_VERSION; }
+const char* cf_last_error(void) { return cf::t_error.c_str(); }
+
+int cf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t cf_launch_count(void) { return (int64_t)cf::g_launches.load(); }
+
+int cf_model_num_tensors(const cf_model_desc* desc) {
+    if (!desc) { cf::set_error("desc is NULL"); return CF_ERR_BAD_ARG; }
+    std::vector<std::vector<int64_t>> shapes;
+    int s = cf::expected_tensor_shapes(*desc, &shapes);
+    if (s != CF_OK) return s;
+    return (int)shapes.size();
+}
+
+int cf_model_create(const cf_model_desc* desc, const float* const* tensors, const int64_t* tensor_sizes,
+                    int32_t n_tensors, int32_t device, cf_model** out_model) {
+    if (!desc || !tensors || !tensor_sizes || !out_model) {
+        cf::set_error("cf_model_create: NULL argument");
+        return CF_ERR_BAD_ARG;
+    }
+    *out_model = nullptr;
+    std::vector<std::vector<int64_t>> shapes;
+    CF_TRY(cf::expected_tensor_shapes(*desc, &shapes));
+    if ((size_t)n_tensors != shapes.size()) {
+        cf::set_error("cf_model_create: expected %zu tensors, got %d", shapes.size(), n_tensors);
+        return CF_ERR_BAD_ARG;
+    }
+    for (size_t i = 0; i < shapes.size(); ++i) {
+        int64_t n = 1;
+        for (int64_t v : shapes[i]) n *= v;
+        if (tensor_sizes[i] != n || !tensors[i]) {
+            cf::set_error("cf_model_create: tensor %zu has %lld elements, expected %lld", i,
+                          (long long)tensor_sizes[i], (long long)n);
+            return CF_ERR_BAD_ARG;
+        }
+    }
+    CF_TRY(cf::use_device(device));
+    cf_model* m = new cf_model();
+    m->device = device;
+    cf::build_host_model(*desc, tensors, &m->hm);
+    int engine = desc->engine;
+    if (engine == CF_ENGINE_AUTO) engine = cf::tc_supported(m->hm) ? CF_ENGINE_TCGEN05 : CF_ENGINE_SIMT;
+    if (engine == CF_ENGINE_TCGEN05 && !cf::tc_supported(m->hm)) {
+        cf::set_error("the tcgen05 engine supports layer_size_res 32 / layer_size 64 only");
+        delete m;
+        return CF_ERR_BAD_ARG;
+    }
+    m->engine = engine;
+    if (engine == CF_ENGINE_TCGEN05) m->tc = cf::tc_create(m->hm);
+    else m->simt = cf::simt_create(m->hm);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess || (!m->tc && !m->simt)) {
+        cf::set_error("cf_model_create: uploading weights failed: %s", cudaGetErrorString(e));
+        cf_model_destroy(m);
+        return CF_ERR_CUDA;
+    }
+    *out_model = m;
+    return CF_OK;
+}
+
+void cf_model_destroy(cf_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    cf::simt_destroy(m->simt);
+    cf::tc_destroy(m->tc);
+    m->pin_plan.release(); m->plan_dev.release(); m->stats.release(); m->wide_flags.release();
+    m->wide_scratch.release(); m->tab_src.release(); m->tab_valid.release(); m->tab_read.release();
+    m->probs_internal.release();
+    m->k6.bits.release(); m->k6.block_cnt.release(); m->k6.read_cnt.release(); m->k6.misc.release();
+    m->h_raw.release(); m->h_intervals.release(); m->h_ioff.release(); m->h_probs.release();
+    m->pin_io.release();
+    if (m->plan_copied) cudaEventDestroy(m->plan_copied);
+    delete m;
+}
+
+int cf_model_engine(const cf_model* m) { return m ? m->engine : CF_ERR_BAD_ARG; }
+
+int cf_model_reserve(cf_model* m, int64_t max_samples, int32_t max_reads) {
+    if (!m || max_samples < 0 || max_reads < 0) { cf::set_error("cf_model_reserve: bad argument"); return CF_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    CF_TRY(cf::use_device(m->device));
+    const int64_t windows = max_samples / cf::kWindow + max_reads;
+    const int64_t tiles = cf::ceil_div(windows, cf::kTileWindows);
+    cf::WindowTable tab;
+    CF_TRY(cf::ensure_table(m, tiles, &tab));
+    CF_TRY(m->stats.ensure(sizeof(double) * 2 * (size_t)max_reads));
+    CF_TRY(m->wide_flags.ensure(sizeof(int32_t) * (size_t)max_reads));
+    CF_TRY(m->wide_scratch.ensure(cf::k1_wide_scratch_bytes(cf::kWideSlots)));
+    CF_TRY(m->probs_internal.ensure(sizeof(float) * (size_t)max_samples));
+    return CF_OK;
+}
+
+int cf_infer_windows(cf_model* m, const float* x_dev, int64_t n_windows, float* probs_dev, void* stream) {
+    if (!m || n_windows < 0 || (n_windows > 0 && (!x_dev || !probs_dev))) {
+        cf::set_error("cf_infer_windows: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    if (n_windows == 0) return CF_OK;
+    std::lock_guard<std::mutex> lock(m->mu);
+    CF_TRY(cf::use_device(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t tiles = cf::ceil_div(n_windows, cf::kTileWindows);
+    cf::WindowTable tab;
+    CF_TRY(cf::ensure_table(m, tiles, &tab));
+    const int64_t slots = tiles * cf::kTileWindows;
+    cf::dense_window_table_kernel<<<(unsigned)cf::ceil_div(slots, 256), 256, 0, st>>>(n_windows, slots, tab.src, tab.valid, tab.read);
+    CF_LAUNCHED();
+    return cf::engine_forward(m, nullptr, nullptr, x_dev, tab, tiles, probs_dev, st);
+}
+
+int cf_infer_reads(cf_model* m, const int16_t* raw_dev, const int64_t* offsets_host, int32_t n_reads,
+                   float* probs_dev, int64_t* intervals_dev, int64_t* interval_offsets_dev,
+                   int64_t capacity, double threshold, int32_t min_run, int32_t ext_left,
+                   int32_t ext_right, void* stream) {
+    if (!m || n_reads < 0 || !offsets_host || !interval_offsets_dev || capacity < 0 ||
+        (n_reads > 0 && !raw_dev) || (capacity > 0 && !intervals_dev)) {
+        cf::set_error("cf_infer_reads: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    std::lock_guard<std::mutex> lock(m->mu);
+    CF_TRY(cf::use_device(m->device));
+    return cf::infer_reads_device(m, raw_dev, offsets_host, n_reads, probs_dev, intervals_dev,
+                                  interval_offsets_dev, capacity, threshold, min_run, ext_left,
+                                  ext_right, static_cast<cudaStream_t>(stream));
+}
+
+int64_t cf_max_intervals(int64_t total_samples, int32_t n_reads, int32_t min_run) {
+    if (total_samples < 0 || n_reads < 0) return 0;
+    const int64_t mr = min_run < 1 ? 1 : min_run;
+    // a run of >= mr ones needs a zero (or a read boundary) before the next one
+    return total_samples / (mr + 1) + n_reads + 1;
+}
+
+int cf_infer_reads_host(cf_model* m, const int16_t* raw_host, const int64_t* offsets_host, int32_t n_reads,
+                        float* probs_host, int64_t* intervals_host, int64_t* interval_offsets_host,
+                        int64_t capacity, double threshold, int32_t min_run, int32_t ext_left,
+                        int32_t ext_right, int64_t* n_intervals_out, void* stream) {
+    if (!m || n_reads < 0 || !offsets_host || !interval_offsets_host || capacity < 0 ||
+        (n_reads > 0 && !raw_host) || (capacity > 0 && !intervals_host)) {
+        cf::set_error("cf_infer_reads_host: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    std::lock_guard<std::mutex> lock(m->mu);
+    CF_TRY(cf::use_device(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t base = n_reads > 0 ? offsets_host[0] : 0;
+    const int64_t total = n_reads > 0 ? offsets_host[n_reads] - base : 0;
+    if (total < 0) { cf::set_error("cf_infer_reads_host: offsets decrease"); return CF_ERR_BAD_ARG; }
+    CF_TRY(m->h_raw.ensure(sizeof(int16_t) * (size_t)(total > 0 ? total : 1)));
+    CF_TRY(m->h_intervals.ensure(sizeof(int64_t) * 2 * (size_t)(capacity > 0 ? capacity : 1)));
+    CF_TRY(m->h_ioff.ensure(sizeof(int64_t) * ((size_t)n_reads + 1)));
+    float* probs_dev = nullptr;
+    if (probs_host) {
+        CF_TRY(m->h_probs.ensure(sizeof(float) * (size_t)(total > 0 ? total : 1)));
+        probs_dev = m->h_probs.as<float>();
+    }
+    if (total > 0)
+        CF_CUDA(cudaMemcpyAsync(m->h_raw.ptr, raw_host + base, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, st));
+    // offsets rebased so that raw_dev + offsets[0] is the staged copy
+    std::vector<int64_t> off((size_t)n_reads + 1);
+    for (int32_t i = 0; i <= n_reads; ++i) off[i] = offsets_host[i] - base;
+    CF_TRY(cf::infer_reads_device(m, m->h_raw.as<int16_t>(), off.data(), n_reads, probs_dev,
+                                  m->h_intervals.as<int64_t>(), m->h_ioff.as<int64_t>(), capacity, threshold,
+                                  min_run, ext_left, ext_right, st));
+    CF_CUDA(cudaMemcpyAsync(interval_offsets_host, m->h_ioff.ptr, sizeof(int64_t) * ((size_t)n_reads + 1),
+                            cudaMemcpyDeviceToHost, st));
+    CF_CUDA(cudaStreamSynchronize(st));
+    const int64_t found = interval_offsets_host[n_reads];
+    if (n_intervals_out) *n_intervals_out = found;
+    const int64_t ncopy = found < capacity ? found : capacity;
+    if (ncopy > 0)
+        CF_CUDA(cudaMemcpyAsync(intervals_host, m->h_intervals.ptr, sizeof(int64_t) * 2 * (size_t)ncopy,
+                                cudaMemcpyDeviceToHost, st));
+    if (probs_host && total > 0)
+        CF_CUDA(cudaMemcpyAsync(probs_host, probs_dev, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    CF_CUDA(cudaStreamSynchronize(st));
+    if (found > capacity) {
+        cf::set_error("cf_infer_reads_host: %lld intervals found, capacity %lld", (long long)found, (long long)capacity);
+        return CF_ERR_CAPACITY;
+    }
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------- model-free helpers
+namespace {
+struct TempBufs {
+    std::vector<cf::DevBuf*> bufs;
+    ~TempBufs() { for (auto* b : bufs) { b->release(); delete b; } }
+    cf::DevBuf* make() { bufs.push_back(new cf::DevBuf()); return bufs.back(); }
+};
+
+int upload_offsets(const int64_t* offsets_host, int32_t n_reads, cf::DevBuf* buf, cudaStream_t st) {
+    CF_TRY(buf->ensure(sizeof(int64_t) * ((size_t)n_reads + 1)));
+    std::vector<int64_t> off((size_t)n_reads + 1);
+    for (int32_t i = 0; i <= n_reads; ++i) off[i] = offsets_host[i] - offsets_host[0];
+    CF_CUDA(cudaMemcpyAsync(buf->ptr, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, st));
+    CF_CUDA(cudaStreamSynchronize(st));     // `off` is pageable and about to go out of scope
+    return CF_OK;
+}
+}  // namespace
+
+int cf_normalize_reads(int32_t device, const int16_t* raw_dev, const int64_t* offsets_host, int32_t n_reads,
+                       double* stats_dev, double* norm_dev, void* stream) {
+    if (n_reads < 0 || !offsets_host || (n_reads > 0 && !raw_dev)) {
+        cf::set_error("cf_normalize_reads: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    if (n_reads == 0) return CF_OK;
+    CF_TRY(cf::use_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int32_t r = 0; r < n_reads; ++r)
+        if (offsets_host[r + 1] < offsets_host[r]) { cf::set_error("cf_normalize_reads: offsets decrease"); return CF_ERR_BAD_ARG; }
+    TempBufs tmp;
+    cf::DevBuf* off = tmp.make();
+    CF_TRY(upload_offsets(offsets_host, n_reads, off, st));
+    cf::DevBuf* flags = tmp.make();
+    cf::DevBuf* wide = tmp.make();
+    cf::DevBuf* stats_tmp = tmp.make();
+    CF_TRY(flags->ensure(sizeof(int32_t) * (size_t)n_reads));
+    CF_TRY(wide->ensure(cf::k1_wide_scratch_bytes(cf::kWideSlots)));
+    double* stats = stats_dev;
+    if (!stats) {
+        CF_TRY(stats_tmp->ensure(sizeof(double) * 2 * (size_t)n_reads));
+        stats = stats_tmp->as<double>();
+    }
+    const int16_t* raw0 = raw_dev + offsets_host[0];
+    CF_TRY(cf::k1_read_stats(raw0, off->as<int64_t>(), n_reads, stats, flags->as<int32_t>(),
+                             wide->as<uint32_t>(), cf::kWideSlots, st));
+    if (norm_dev)
+        CF_TRY(cf::k1_normalize_f64(raw0, off->as<int64_t>(), n_reads, offsets_host[n_reads] - offsets_host[0],
+                                    stats, norm_dev, st));
+    CF_CUDA(cudaStreamSynchronize(st));      // scratch is freed on return
+    return CF_OK;
+}
+
+int cf_call_intervals(int32_t device, const void* probs_dev, int32_t probs_is_f64, const int64_t* offsets_host,
+                      int32_t n_reads, int64_t* intervals_dev, int64_t* interval_offsets_dev, int64_t capacity,
+                      double threshold, int32_t min_run, int32_t ext_left, int32_t ext_right, void* stream) {
+    if (n_reads < 0 || !offsets_host || !interval_offsets_dev || capacity < 0 || (capacity > 0 && !intervals_dev)) {
+        cf::set_error("cf_call_intervals: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    CF_TRY(cf::use_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_reads == 0) {
+        CF_CUDA(cudaMemsetAsync(interval_offsets_dev, 0, sizeof(int64_t), st));
+        return CF_OK;
+    }
+    for (int32_t r = 0; r < n_reads; ++r)
+        if (offsets_host[r + 1] < offsets_host[r]) { cf::set_error("cf_call_intervals: offsets decrease"); return CF_ERR_BAD_ARG; }
+    const int64_t total = offsets_host[n_reads] - offsets_host[0];
+    if (total > 0 && !probs_dev) { cf::set_error("cf_call_intervals: probs is NULL"); return CF_ERR_BAD_ARG; }
+    TempBufs tmp;
+    cf::DevBuf* off = tmp.make();
+    CF_TRY(upload_offsets(offsets_host, n_reads, off, st));
+    cf::IntervalScratch scratch;
+    const char* base = static_cast<const char*>(probs_dev) + (size_t)offsets_host[0] * (probs_is_f64 ? 8 : 4);
+    int s = cf::k6_call_intervals(scratch, base, probs_is_f64 ? cf::BITS_FROM_F64 : cf::BITS_FROM_F32, threshold, 1,
+                                  off->as<int64_t>(), n_reads, total, intervals_dev, interval_offsets_dev, nullptr,
+                                  capacity, min_run, ext_left, ext_right, st);
+    cudaStreamSynchronize(st);
+    scratch.bits.release(); scratch.block_cnt.release(); scratch.read_cnt.release(); scratch.misc.release();
+    return s;
+}
+
+int cf_class_from_threshold(int32_t device, const double* scores_dev, int64_t n, double threshold,
+                            int64_t* labels_dev, void* stream) {
+    if (n < 0 || (n > 0 && (!scores_dev || !labels_dev))) { cf::set_error("cf_class_from_threshold: bad argument"); return CF_ERR_BAD_ARG; }
+    CF_TRY(cf::use_device(device));
+    return cf::k6_class_from_threshold(scores_dev, n, threshold, labels_dev, static_cast<cudaStream_t>(stream));
+}
+
+int cf_correct_short(int32_t device, const int64_t* labels_dev, int64_t n, int32_t threshold, int64_t* out_dev,
+                     void* stream) {
+    if (n < 0 || (n > 0 && (!labels_dev || !out_dev)) || labels_dev == out_dev && n > 0) {
+        cf::set_error("cf_correct_short: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    CF_TRY(cf::use_device(device));
+    return cf::k6_correct_short(labels_dev, n, threshold, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int cf_hp_in_pred(int32_t device, const int64_t* labels_dev, int64_t n, int32_t ext_left, int32_t ext_right,
+                  int64_t label, int64_t* intervals_dev, int64_t capacity, int64_t* n_out_dev, void* stream) {
+    if (n < 0 || capacity < 0 || !n_out_dev || (n > 0 && !labels_dev) || (capacity > 0 && !intervals_dev)) {
+        cf::set_error("cf_hp_in_pred: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    if (n == 0) { cf::set_error("cf_hp_in_pred: empty input (the reference raises IndexError, infer.py:151)"); return CF_ERR_EMPTY_READ; }
+    CF_TRY(cf::use_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TempBufs tmp;
+    cf::DevBuf* off = tmp.make();
+    cf::DevBuf* ioff = tmp.make();
+    const int64_t offsets[2] = {0, n};
+    CF_TRY(upload_offsets(offsets, 1, off, st));
+    CF_TRY(ioff->ensure(sizeof(int64_t) * 2));
+    cf::IntervalScratch scratch;
+    int s = cf::k6_call_intervals(scratch, labels_dev, cf::BITS_FROM_I64_EQ, 0.0, label, off->as<int64_t>(), 1, n,
+                                  intervals_dev, ioff->as<int64_t>(), n_out_dev, capacity, 1, ext_left, ext_right, st);
+    cudaStreamSynchronize(st);
+    scratch.bits.release(); scratch.block_cnt.release(); scratch.read_cnt.release(); scratch.misc.release();
+    return s;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Shared declarations of the catfish_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/catfish_b200.h"
+
+namespace cf {
+
+constexpr int kWindow = 35;        // rnn_class.py:27
+constexpr int kTileWindows = 128;  // windows per tile = TMEM lanes = UMMA M
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define CF_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            cf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                          __FILE__, __LINE__);                                          \
+            return CF_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define CF_TRY(expr)                 \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != CF_OK) return _s;  \
+    } while (0)
+
+// Counts the launch and checks the launch error.
+#define CF_LAUNCHED()                                                                   \
+    do {                                                                                \
+        cf::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) {                                                        \
+            cf::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                          __FILE__, __LINE__);                                          \
+            return CF_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---------------------------------------------------------------- device buffers
+// A growable device allocation owned by a handle; grows only when asked for more.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// Pinned host staging buffer.
+struct HostBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// ---------------------------------------------------------------- ragged batch plan
+// Host-side description of one ragged batch of reads, and its device mirrors.
+struct BatchPlan {
+    int32_t n_reads = 0;
+    int64_t total_samples = 0;
+    int64_t total_windows = 0;     // sum over reads of L/35 + 1   (infer.py:32-38)
+    int64_t n_tiles = 0;           // ceil(total_windows / 128)
+    std::vector<int64_t> win_off;  // [R+1] first global window of each read
+};
+
+// Device arrays describing the windows of a batch (built by k1).
+struct WindowTable {
+    int64_t* src = nullptr;    // [n_tiles*128] first raw sample of the window, -1 = filler window
+    int32_t* valid = nullptr;  // [n_tiles*128] real samples in the window (0..35)
+    int32_t* read = nullptr;   // [n_tiles*128] read index, -1 = filler window
+};
+
+// ---------------------------------------------------------------- k1: normalisation
+int k1_read_stats(const int16_t* raw, const int64_t* offsets_dev, int32_t n_reads, double* stats,
+                  int32_t* wide_flags, uint32_t* wide_scratch, int n_wide_slots,
+                  cudaStream_t stream);
+int k1_normalize_f64(const int16_t* raw, const int64_t* offsets_dev, int32_t n_reads,
+                     int64_t total_samples, const double* stats, double* norm,
+                     cudaStream_t stream);
+int k1_window_table(const int64_t* offsets_dev, const int64_t* win_off_dev, int32_t n_reads,
+                    int64_t total_windows, int64_t n_tiles, WindowTable tab, cudaStream_t stream);
+size_t k1_wide_scratch_bytes(int n_slots);
+
+// ---------------------------------------------------------------- k6: interval calling
+struct IntervalScratch {
+    DevBuf bits;        // label bit words
+    DevBuf block_cnt;   // per-block counts + scanned bases
+    DevBuf read_cnt;    // per-read counts
+    DevBuf misc;
+};
+enum BitSource { BITS_FROM_F32 = 0, BITS_FROM_F64 = 1, BITS_FROM_I64_EQ = 2 };
+int k6_call_intervals(IntervalScratch& s, const void* values, int source, double threshold,
+                      int64_t label, const int64_t* offsets_dev, int32_t n_reads,
+                      int64_t total_samples, int64_t* intervals, int64_t* interval_offsets,
+                      int64_t* total_out, int64_t capacity, int32_t min_run, int32_t ext_left,
+                      int32_t ext_right, cudaStream_t stream);
+int k6_class_from_threshold(const double* scores, int64_t n, double threshold, int64_t* labels,
+                            cudaStream_t stream);
+int k6_correct_short(const int64_t* labels, int64_t n, int32_t threshold, int64_t* out,
+                     cudaStream_t stream);
+
+}  // namespace cf

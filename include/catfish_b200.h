@@ -1,0 +1,184 @@
+/*
+ * catfish_b200.h - C ABI of the B200-native catfish inference hot path.
+ *
+ * Every entry point is plain C: pointers, sizes, scalars.  No torch types, no
+ * exceptions across the boundary.  Functions return 0 on success or a negative
+ * cf_status; cf_last_error() gives the message of the last failure on the
+ * calling thread.  Unless stated otherwise "dev" pointers are CUDA device
+ * pointers on the model's device, "host" pointers are ordinary host memory, and
+ * work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default
+ * stream) without synchronising.
+ *
+ * Each function names the reference interface it replaces (paths relative to
+ * the catfish repository root).
+ */
+#ifndef CATFISH_B200_H
+#define CATFISH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CF_ABI_VERSION 1
+
+typedef enum cf_status {
+    CF_OK = 0,
+    CF_ERR_BAD_ARG = -1,      /* NULL pointer, negative size, unsupported hyper-parameter */
+    CF_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+    CF_ERR_NO_DEVICE = -3,    /* no usable sm_100 device: there is no CPU fallback */
+    CF_ERR_EMPTY_READ = -4,   /* a read of length 0: the reference raises IndexError (infer.py:151,184) */
+    CF_ERR_CAPACITY = -5,     /* an output buffer is too small */
+    CF_ERR_ALLOC = -6         /* workspace allocation failed */
+} cf_status;
+
+typedef enum cf_network_type {
+    CF_NET_RESNET_RNN = 0,    /* models/resnet_class.py:7-25  */
+    CF_NET_RNN = 1,           /* models/rnn_class.py:9-54 used directly (neural_network.py:17-18) */
+    CF_NET_RESNET = 2         /* resnet_class.py:23 commented out: conv stack -> dense */
+} cf_network_type;
+
+typedef enum cf_engine {
+    CF_ENGINE_AUTO = 0,       /* tcgen05 kernels when the shape is supported, else SIMT */
+    CF_ENGINE_TCGEN05 = 1,    /* bf16x3 split operands on tcgen05/TMEM (C = 32, H = 64) */
+    CF_ENGINE_SIMT = 2        /* fp32 CUDA-core kernels, any shape (on-device cross-check) */
+} cf_engine;
+
+/* Hyper-parameters: the constructor kwargs of RNN / ResNetRNN
+ * (models/rnn_class.py:10-31, models/resnet_class.py:9-14, neural_network.py:37-67). */
+typedef struct cf_model_desc {
+    int32_t network_type;     /* cf_network_type */
+    int32_t window;           /* 35, rnn_class.py:27 */
+    int32_t layer_size;       /* GRU units H */
+    int32_t n_layers;         /* stacked bidirectional GRU layers */
+    int32_t layer_size_res;   /* conv channels C */
+    int32_t n_layers_res;     /* residual blocks */
+    float bn_epsilon;         /* 1e-3 */
+    int32_t engine;           /* cf_engine */
+} cf_model_desc;
+
+typedef struct cf_model cf_model;
+
+/* Library / device probes. */
+int cf_abi_version(void);
+const char* cf_last_error(void);
+int cf_device_count(void);
+
+/*
+ * cf_model_create - replaces RNN.__init__ + restore_network
+ * (models/rnn_class.py:10-54, 191-198; neural_network.py:8-34).
+ * `tensors` are host float32 arrays in TensorFlow layout, in this order:
+ *   per residual block b, per conv j = 0..3 (shortcut k1, conv k1, conv k3, conv k1):
+ *       conv1d_{4b+j}/kernel [K,Cin,Cout], /bias [Cout],
+ *       batch_normalization_{4b+j}/gamma, /beta, /moving_mean, /moving_variance [Cout]
+ *   per GRU layer l, per direction fw then bw:
+ *       gates/kernel [in+H,2H], gates/bias [2H], candidate/kernel [in+H,H], candidate/bias [H]
+ *   final_fully_connected/kernel [F,1], /bias [1]
+ * `tensor_sizes[i]` is the element count of tensors[i] and is checked against the
+ * shape the descriptor implies.  Weights are folded/re-packed once, here.
+ */
+int cf_model_create(const cf_model_desc* desc, const float* const* tensors,
+                    const int64_t* tensor_sizes, int32_t n_tensors, int32_t device,
+                    cf_model** out_model);
+void cf_model_destroy(cf_model* model);
+
+/* Number of weight tensors cf_model_create expects for `desc` (negative on bad desc). */
+int cf_model_num_tensors(const cf_model_desc* desc);
+
+/* Which engine the handle resolved to (cf_engine value). */
+int cf_model_engine(const cf_model* model);
+
+/* Pre-size the handle's workspace so later calls do not allocate
+ * (max total samples / reads per call).  Optional. */
+int cf_model_reserve(cf_model* model, int64_t max_samples, int32_t max_reads);
+
+/*
+ * cf_infer_windows - replaces RNN.infer / ResNetRNN.infer
+ * (models/rnn_class.py:213-219, called from infer.py:44).
+ * x_dev:     float32 [n_windows, 35] (the [B,35,1] placeholder feed), device
+ * probs_dev: float32 [n_windows * 35], window-major then position, device
+ */
+int cf_infer_windows(cf_model* model, const float* x_dev, int64_t n_windows,
+                     float* probs_dev, void* stream);
+
+/*
+ * cf_infer_reads - replaces infer.infer_class_from_signal (infer.py:12-51) for a
+ * ragged batch of reads whose raw signal is already on the device (the FAST5
+ * decode of process_signal, infer.py:77-90, stays on the host).
+ *   raw_dev          int16, reads concatenated, device
+ *   offsets_host     int64 [n_reads+1], host; read r = raw[offsets[r] : offsets[r+1]]
+ *   probs_dev        float32 [total samples] or NULL: per-position probabilities with the
+ *                    padding already cut (infer.py:47), in read order
+ *   intervals_dev    int64 [capacity][2]: [start - ext_left, start + len + ext_right) of every
+ *                    positive run of length >= min_run, read-local coordinates, unclamped,
+ *                    unmerged, increasing start (infer.py:48-49, 141-162, 174-198)
+ *   interval_offsets_dev int64 [n_reads+1]: CSR offsets of each read's intervals;
+ *                    element n_reads is the total (compare with capacity)
+ *   threshold        class_from_threshold's threshold (infer.py:128), compared in double
+ * Defaults of the reference: threshold 0.5, min_run 15, ext_left 11, ext_right 16.
+ */
+int cf_infer_reads(cf_model* model, const int16_t* raw_dev, const int64_t* offsets_host,
+                   int32_t n_reads, float* probs_dev, int64_t* intervals_dev,
+                   int64_t* interval_offsets_dev, int64_t capacity, double threshold,
+                   int32_t min_run, int32_t ext_left, int32_t ext_right, void* stream);
+
+/*
+ * cf_infer_reads_host - the same call with HOST buffers: copies the signal to the
+ * device, runs cf_infer_reads, copies results back and synchronises.  This is the
+ * end-to-end path the Python per-read entry points use.  probs_host may be NULL.
+ * *n_intervals_out receives the total number of intervals found; if it exceeds
+ * `capacity` the call returns CF_ERR_CAPACITY after filling the first `capacity`.
+ */
+int cf_infer_reads_host(cf_model* model, const int16_t* raw_host, const int64_t* offsets_host,
+                        int32_t n_reads, float* probs_host, int64_t* intervals_host,
+                        int64_t* interval_offsets_host, int64_t capacity, double threshold,
+                        int32_t min_run, int32_t ext_left, int32_t ext_right,
+                        int64_t* n_intervals_out, void* stream);
+
+/* Upper bound on the number of intervals cf_infer_reads can emit. */
+int64_t cf_max_intervals(int64_t total_samples, int32_t n_reads, int32_t min_run);
+
+/*
+ * cf_normalize_reads - replaces infer.normalize_raw_signal(raw, "median")
+ * (infer.py:96-105; duplicate networks/trainingDB/helper_functions.py:87-98).
+ *   stats_dev  double [n_reads][2] = (shift, scale) = (median, median |raw - median|), or NULL
+ *   norm_dev   double [total samples] = (raw - shift) / scale, or NULL
+ * Needs no model: pass device explicitly.  Scratch is allocated and freed inside.
+ */
+int cf_normalize_reads(int32_t device, const int16_t* raw_dev, const int64_t* offsets_host,
+                       int32_t n_reads, double* stats_dev, double* norm_dev, void* stream);
+
+/*
+ * cf_call_intervals - threshold + short-run removal + interval emission on given
+ * probabilities: class_from_threshold -> correct_short -> hp_in_pred
+ * (infer.py:128-138, 174-198, 141-162) for a ragged batch.  Arguments as cf_infer_reads;
+ * probs_dev is float32 (probs_is_f64 = 0) or float64 (1).
+ */
+int cf_call_intervals(int32_t device, const void* probs_dev, int32_t probs_is_f64,
+                      const int64_t* offsets_host, int32_t n_reads, int64_t* intervals_dev,
+                      int64_t* interval_offsets_dev, int64_t capacity, double threshold,
+                      int32_t min_run, int32_t ext_left, int32_t ext_right, void* stream);
+
+/* class_from_threshold (infer.py:128-138): labels[i] = scores[i] >= threshold ? 1 : 0. */
+int cf_class_from_threshold(int32_t device, const double* scores_dev, int64_t n, double threshold,
+                            int64_t* labels_dev, void* stream);
+
+/* correct_short (infer.py:174-198): every run of equal non-zero labels shorter than
+ * `threshold` becomes 0.  in/out may not alias. */
+int cf_correct_short(int32_t device, const int64_t* labels_dev, int64_t n, int32_t threshold,
+                     int64_t* out_dev, void* stream);
+
+/* hp_in_pred (infer.py:141-162): [start - ext_left, start + len + ext_right] for every run
+ * of `label`.  *n_out_dev (device int64) receives the count; at most `capacity` are written. */
+int cf_hp_in_pred(int32_t device, const int64_t* labels_dev, int64_t n, int32_t ext_left,
+                  int32_t ext_right, int64_t label, int64_t* intervals_dev, int64_t capacity,
+                  int64_t* n_out_dev, void* stream);
+
+/* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t cf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATFISH_B200_H */

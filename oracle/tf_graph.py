@@ -1,0 +1,231 @@
+"""ORACLE (test infrastructure, not product code): CPU restatement of the catfish forward graph.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module; the product package
+``catfish_b200`` never does.
+
+TensorFlow 1.10 (the version pinned by the shipped meta-graph,
+``meta_info_def.tensorflow_version = "1.10.0"``) is not installed here and is not
+vendored in /root/reference, so the arithmetic of the reference's
+``sess.run(self.predictions)`` is restated op by op from the reference's model
+code and the shipped ``ckpnt-30000.meta`` graph:
+
+* residual blocks        /root/reference/catfish/models/resnet_class.py:17-25, 44-82
+* bidirectional GRU      /root/reference/catfish/models/rnn_class.py:142-175
+* dense + sigmoid        /root/reference/catfish/models/rnn_class.py:178-183, 84
+* flatten / cast         /root/reference/catfish/models/rnn_class.py:213-219
+
+Pinning: the reference holds no tests, golden vectors or fixtures for this path
+(SURVEY.md section 4), and TensorFlow cannot be run here, so the network part
+of this oracle is pinned only by the graph/weight spec -> "parity unpinned" for
+the probabilities.  The integer pre/post-processing (oracle/postprocess.py) IS
+pinned against the reference's own ``catfish/infer.py`` functions imported
+unmodified (oracle/ref_infer.py, tests/test_oracle_vs_reference.py).
+
+Two arithmetic flavours of the same op sequence:
+
+* ``forward_np``    numpy, any dtype (float64 = accuracy oracle)
+* ``forward_torch`` torch-CPU float32, all host threads (the timed CPU baseline)
+"""
+
+import numpy as np
+
+WINDOW = 35
+BN_EPSILON = 1e-3
+
+
+def _suffix(i):
+    return "" if i == 0 else "_%d" % i
+
+
+def _gru_prefix(layer, direction):
+    return "stack_bidirectional_rnn/cell_%d/bidirectional_rnn/%s/gru_cell" % (layer, direction)
+
+
+def describe(weights):
+    """Infer (network_type, n_layers_res, n_layers) from the variable names."""
+    n_res = 0
+    while "conv1d%s/kernel" % _suffix(4 * n_res) in weights:
+        n_res += 1
+    n_rnn = 0
+    while _gru_prefix(n_rnn, "fw") + "/gates/kernel" in weights:
+        n_rnn += 1
+    if n_res and n_rnn:
+        kind = "ResNetRNN"
+    elif n_rnn:
+        kind = "RNN"
+    else:
+        kind = "ResNet"
+    return kind, n_res, n_rnn
+
+
+# ----------------------------------------------------------------------------- numpy
+
+def _sigmoid_np(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def _conv1d_same_np(x, kernel, bias):
+    """tf.layers.conv1d(padding="same"), stride 1 (resnet_class.py:60,64,69,74).
+
+    x [B, T, Cin]; kernel [K, Cin, Cout]; zero padding inside each window."""
+    k = kernel.shape[0]
+    pad = (k - 1) // 2
+    b, t, _ = x.shape
+    xp = np.zeros((b, t + 2 * pad, x.shape[2]), x.dtype)
+    xp[:, pad:pad + t] = x
+    y = np.zeros((b, t, kernel.shape[2]), x.dtype)
+    for j in range(k):
+        y += xp[:, j:j + t] @ kernel[j]
+    return y + bias
+
+
+def _batch_norm_np(x, w, i):
+    """tf.layers.batch_normalization with training=False (resnet_class.py:61,65,70,75):
+    ops add, Rsqrt, mul, mul_1, mul_2, sub, add_1 of the shipped graph."""
+    n = "batch_normalization" + _suffix(i)
+    dt = x.dtype
+    inv = 1.0 / np.sqrt(w[n + "/moving_variance"].astype(dt) + dt.type(BN_EPSILON))
+    scale = inv * w[n + "/gamma"].astype(dt)
+    return x * scale + (w[n + "/beta"].astype(dt) - w[n + "/moving_mean"].astype(dt) * scale)
+
+
+def _residual_block_np(x, w, b):
+    """resnet_class.py:44-82; block b uses conv1d_{4b..4b+3}, batch_normalization_{4b..4b+3}."""
+    dt = x.dtype
+
+    def conv(i, inp):
+        n = "conv1d" + _suffix(i)
+        return _conv1d_same_np(inp, w[n + "/kernel"].astype(dt), w[n + "/bias"].astype(dt))
+
+    i = 4 * b
+    sc = _batch_norm_np(conv(i, x), w, i)
+    o = np.maximum(_batch_norm_np(conv(i + 1, x), w, i + 1), 0)
+    o = np.maximum(_batch_norm_np(conv(i + 2, o), w, i + 2), 0)
+    o = np.maximum(_batch_norm_np(conv(i + 3, o), w, i + 3), 0)
+    return np.maximum(o + sc, 0)
+
+
+def _gru_direction_np(x, w, prefix, reverse):
+    """tf.contrib.rnn.GRUCell unrolled by dynamic_rnn from a zero state
+    (rnn_class.py:146,170-171): reset gate applied BEFORE the candidate matmul."""
+    dt = x.dtype
+    wg = w[prefix + "/gates/kernel"].astype(dt)
+    bg = w[prefix + "/gates/bias"].astype(dt)
+    wc = w[prefix + "/candidate/kernel"].astype(dt)
+    bc = w[prefix + "/candidate/bias"].astype(dt)
+    hsz = wc.shape[1]
+    b, t, _ = x.shape
+    h = np.zeros((b, hsz), dt)
+    out = np.zeros((b, t, hsz), dt)
+    steps = range(t - 1, -1, -1) if reverse else range(t)
+    for s in steps:
+        xs = x[:, s]
+        g = _sigmoid_np(np.concatenate([xs, h], axis=1) @ wg + bg)
+        r, u = g[:, :hsz], g[:, hsz:]
+        c = np.tanh(np.concatenate([xs, r * h], axis=1) @ wc + bc)
+        h = u * h + (1 - u) * c
+        out[:, s] = h
+    return out
+
+
+def forward_np(weights, x, dtype=np.float64, return_logits=False):
+    """x [B, 35, 1] -> probabilities [B*35] (window-major, then position)."""
+    kind, n_res, n_rnn = describe(weights)
+    y = np.asarray(x, np.float32).astype(dtype).reshape(-1, WINDOW, 1)
+    for b in range(n_res):
+        y = _residual_block_np(y, weights, b)
+    for l in range(n_rnn):
+        fw = _gru_direction_np(y, weights, _gru_prefix(l, "fw"), False)
+        bw = _gru_direction_np(y, weights, _gru_prefix(l, "bw"), True)
+        y = np.concatenate([fw, bw], axis=2)
+    logits = y.reshape(-1, y.shape[2]) @ weights["final_fully_connected/kernel"].astype(dtype) \
+        + weights["final_fully_connected/bias"].astype(dtype)
+    logits = logits.reshape(-1)
+    if return_logits:
+        return logits
+    return _sigmoid_np(logits)
+
+
+# ----------------------------------------------------------------------------- torch fp32
+
+class TorchGraph(object):
+    """The same op sequence in torch-CPU float32 with weights converted once."""
+
+    def __init__(self, weights):
+        import torch
+        self.torch = torch
+        self.kind, self.n_res, self.n_rnn = describe(weights)
+        self.w = {k: torch.from_numpy(np.ascontiguousarray(v, np.float32)) for k, v in weights.items()}
+
+    def _bn(self, x, i):
+        t = self.torch
+        n = "batch_normalization" + _suffix(i)
+        w = self.w
+        scale = t.rsqrt(w[n + "/moving_variance"] + BN_EPSILON) * w[n + "/gamma"]
+        return x * scale + (w[n + "/beta"] - w[n + "/moving_mean"] * scale)
+
+    def _conv(self, x, i):
+        t = self.torch
+        n = "conv1d" + _suffix(i)
+        kernel, bias = self.w[n + "/kernel"], self.w[n + "/bias"]
+        k = kernel.shape[0]
+        pad = (k - 1) // 2
+        b, tt, cin = x.shape
+        if pad:
+            xp = t.zeros((b, tt + 2 * pad, cin), dtype=x.dtype)
+            xp[:, pad:pad + tt] = x
+        else:
+            xp = x
+        y = None
+        for j in range(k):
+            term = xp[:, j:j + tt].reshape(-1, cin) @ kernel[j]
+            y = term if y is None else y + term
+        return y.reshape(b, tt, -1) + bias
+
+    def _block(self, x, b):
+        t = self.torch
+        i = 4 * b
+        sc = self._bn(self._conv(x, i), i)
+        o = t.relu(self._bn(self._conv(x, i + 1), i + 1))
+        o = t.relu(self._bn(self._conv(o, i + 2), i + 2))
+        o = t.relu(self._bn(self._conv(o, i + 3), i + 3))
+        return t.relu(o + sc)
+
+    def _gru(self, x, prefix, reverse):
+        t = self.torch
+        wg, bg = self.w[prefix + "/gates/kernel"], self.w[prefix + "/gates/bias"]
+        wc, bc = self.w[prefix + "/candidate/kernel"], self.w[prefix + "/candidate/bias"]
+        hsz = wc.shape[1]
+        b, tt, _ = x.shape
+        h = t.zeros((b, hsz), dtype=x.dtype)
+        out = t.empty((b, tt, hsz), dtype=x.dtype)
+        steps = range(tt - 1, -1, -1) if reverse else range(tt)
+        for s in steps:
+            xs = x[:, s]
+            g = t.sigmoid(t.cat([xs, h], dim=1) @ wg + bg)
+            r, u = g[:, :hsz], g[:, hsz:]
+            c = t.tanh(t.cat([xs, r * h], dim=1) @ wc + bc)
+            h = u * h + (1 - u) * c
+            out[:, s] = h
+        return out
+
+    def infer(self, x):
+        """Mirror of RNN.infer (rnn_class.py:213-219): float64 vector of length B*35."""
+        t = self.torch
+        with t.no_grad():
+            y = t.from_numpy(np.ascontiguousarray(np.asarray(x, np.float32).reshape(-1, WINDOW, 1)))
+            for b in range(self.n_res):
+                y = self._block(y, b)
+            for l in range(self.n_rnn):
+                fw = self._gru(y, _gru_prefix(l, "fw"), False)
+                bw = self._gru(y, _gru_prefix(l, "bw"), True)
+                y = t.cat([fw, bw], dim=2)
+            logits = y.reshape(-1, y.shape[2]) @ self.w["final_fully_connected/kernel"] \
+                + self.w["final_fully_connected/bias"]
+            p = t.sigmoid(logits).reshape(-1)
+        return p.numpy().astype(float)
+
+
+def forward_torch(weights, x):
+    return TorchGraph(weights).infer(x)

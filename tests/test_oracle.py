@@ -1,0 +1,134 @@
+"""CPU: pin the oracle against the reference's own functions and the golden vectors."""
+import numpy as np
+import pytest
+
+from helpers import golden, hpm_from_golden, random_labels
+from catfish_b200 import synth, weights
+from oracle import postprocess, ref_infer, tf_graph
+
+needs_ref = pytest.mark.skipif(not ref_infer.available(), reason="reference tree not mounted")
+
+
+def test_postprocess_against_golden():
+    g = golden("postprocess.npz")
+    for i in range(int(g["n_patterns"])):
+        p = g["pat%d" % i]
+        for fn in (postprocess.correct_short, postprocess.correct_short_loops):
+            np.testing.assert_array_equal(fn(list(p)), g["pat%d_correct_short" % i])
+        for lab in (1, 0):
+            want = g["pat%d_hp_label%d" % (i, lab)].tolist()
+            assert postprocess.hp_in_pred(p, label=lab) == want
+            assert postprocess.hp_in_pred_loops(list(p), label=lab) == want
+        assert postprocess.hp_in_pred(p, 3, 0) == g["pat%d_hp_ext" % i].tolist()
+    s = g["scores"]
+    np.testing.assert_array_equal(postprocess.class_from_threshold(s), g["scores_labels_0.5"])
+    np.testing.assert_array_equal(postprocess.class_from_threshold(s, 0.9), g["scores_labels_0.9"])
+    assert postprocess.class_from_threshold_loops(s) == g["scores_labels_0.5"].tolist()
+    for i in range(int(g["n_raws"])):
+        with np.errstate(all="ignore"):
+            got = postprocess.normalize_raw_signal(g["raw%d" % i])
+        np.testing.assert_array_equal(got, g["raw%d_norm" % i])      # bit-exact, NaN == NaN
+
+
+def test_known_answers_from_survey():
+    # SURVEY.md section 8c, observed on the reference's functions
+    assert postprocess.hp_in_pred([1] * 20 + [0] * 5) == [[-11, 36]]
+    assert postprocess.hp_in_pred([0] * 5 + [1] * 20) == [[-6, 41]]
+    out = postprocess.correct_short([1] * 14 + [0] * 3 + [1] * 15)
+    assert out.tolist() == [0] * 17 + [1] * 15
+    np.testing.assert_array_equal(postprocess.normalize_raw_signal(np.array([1, 2, 3, 4])), [-1.5, -0.5, 0.5, 1.5])
+    assert [postprocess.padding_size(n) for n in (1, 34, 35, 36, 70, 10000)] == [34, 1, 35, 34, 35, 10]
+    with pytest.raises(IndexError):
+        postprocess.hp_in_pred([])
+
+
+@needs_ref
+def test_postprocess_against_reference_functions():
+    ref = ref_infer.load()
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(1, 3000))
+        labels = random_labels(rng, n, p_switch=float(rng.choice([0.02, 0.08, 0.3])))
+        np.testing.assert_array_equal(postprocess.correct_short(labels), ref.correct_short(list(labels)))
+        assert postprocess.hp_in_pred(labels) == ref.hp_in_pred(list(labels))
+        thr = int(rng.integers(1, 40))
+        np.testing.assert_array_equal(postprocess.correct_short(labels, thr), ref.correct_short(list(labels), thr))
+        scores = rng.random(n)
+        assert postprocess.class_from_threshold(scores).tolist() == ref.class_from_threshold(scores)
+        raw = synth.synth_read(n, 900 + trial)
+        with np.errstate(all="ignore"):
+            np.testing.assert_array_equal(postprocess.normalize_raw_signal(raw), ref.normalize_raw_signal(raw, "median"))
+
+
+@needs_ref
+def test_infer_read_matches_reference_driver_logic(shipped_weights):
+    """The oracle's infer_read == the statements of infer_class_from_signal (infer.py:30-51)
+    executed with the reference's own helper functions around the same network callable."""
+    ref = ref_infer.load()
+    g = tf_graph.TorchGraph(shipped_weights)
+    for n in (700, 1225):
+        raw = synth.synth_read(n, 31 + n)
+        norm = ref.normalize_raw_signal(raw, "median")
+        if not (len(norm) / 35).is_integer():
+            pad = 35 - (len(norm) - (len(norm) // 35 * 35))
+        else:
+            pad = 35
+        x = ref.reshape_input(np.hstack((norm, np.array(pad * [0]))), 35, 1)
+        scores = g.infer(x)[:-pad]
+        labels = ref.correct_short(ref.class_from_threshold(scores))
+        want = ref.hp_in_pred(labels)
+        hps, length, got_scores = postprocess.infer_read(raw, g.infer)
+        assert hps == want and length == len(labels) == n
+        np.testing.assert_array_equal(got_scores, scores)
+        hps_loops, _, _ = postprocess.infer_read(raw, g.infer, loops=True)
+        assert hps_loops == want
+
+
+def test_forward_against_golden_shipped(shipped_weights):
+    g = golden("forward_resnetrnn_shipped.npz")
+    graph = tf_graph.TorchGraph(shipped_weights)
+    for i in range(int(g["n_reads"])):
+        raw = g["read%d" % i]
+        hps, length, scores = postprocess.infer_read(raw, graph.infer)
+        assert length == len(raw)
+        assert np.abs(scores - g["read%d_p64" % i]).max() < 2e-6       # fp32 graph vs fp64 graph
+        assert np.abs(scores - g["read%d_p32" % i]).max() < 2e-6       # thread-count dependent summation
+        # intervals: identical unless a probability sits within 1e-6 of the threshold
+        if np.abs(g["read%d_p64" % i] - 0.5).min() > 1e-5:
+            assert hps == g["read%d_hps" % i].tolist()
+        x, pad = postprocess.pad_and_window(postprocess.normalize_raw_signal(raw))
+        p64 = tf_graph.forward_np(shipped_weights, x, np.float64)[:-pad]
+        np.testing.assert_allclose(p64, g["read%d_p64" % i], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["forward_rnn_le64_ns3_seed11.npz", "forward_resnet_ls32_ns2_seed12.npz",
+                                  "forward_rnn_le16_ns2_seed13.npz"])
+def test_forward_against_golden_random_init(name):
+    g = golden(name)
+    w = weights.random_init(str(g["kind"]), seed=int(g["seed"]), **hpm_from_golden(g))
+    p64 = tf_graph.forward_np(w, g["x"], np.float64)
+    np.testing.assert_allclose(p64, g["p64"], rtol=0, atol=1e-12)
+    p32 = tf_graph.forward_torch(w, g["x"])
+    assert np.abs(p32 - g["p64"]).max() < 2e-6
+    assert tf_graph.describe(w)[0] == str(g["kind"])
+
+
+def test_gru_is_reset_before_matmul():
+    """TF GRUCell applies r before the candidate matmul; torch.nn.GRU applies it after."""
+    rng = np.random.default_rng(0)
+    w = weights.random_init("RNN", seed=3, layer_size=8, n_layers=1)
+    x = rng.normal(size=(2, 35, 1)).astype(np.float32)
+    p = tf_graph.forward_np(w, x, np.float64)
+    # hand-rolled single step for window 0, t = 0, forward direction
+    pre = "stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/gru_cell"
+    wg, bg = w[pre + "/gates/kernel"].astype(float), w[pre + "/gates/bias"].astype(float)
+    wc, bc = w[pre + "/candidate/kernel"].astype(float), w[pre + "/candidate/bias"].astype(float)
+    h = np.zeros(8)
+    xs = x[0, 0].astype(float)
+    g_ = 1 / (1 + np.exp(-(np.concatenate([xs, h]) @ wg + bg)))
+    r, u = g_[:8], g_[8:]
+    c = np.tanh(np.concatenate([xs, r * h]) @ wc + bc)
+    h1 = u * h + (1 - u) * c
+    out = tf_graph._gru_direction_np(x.astype(float), w, pre, False)
+    np.testing.assert_allclose(out[0, 0], h1, atol=1e-12)
+    assert p.shape == (70,)

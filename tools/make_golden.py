@@ -1,0 +1,117 @@
+#!/usr/bin/env python3
+"""Generate the golden vectors under tests/golden/ (run in the build container).
+
+    python tools/make_golden.py
+
+Sources of truth:
+* pre/post-processing: the REFERENCE's own functions, imported unmodified from
+  /root/reference/catfish/infer.py (oracle/ref_infer.py) - normalize_raw_signal,
+  class_from_threshold, correct_short, hp_in_pred;
+* network probabilities: the oracle's float64 numpy restatement of the TF graph
+  (oracle/tf_graph.py) on the shipped checkpoint / seeded random-init weights
+  (TensorFlow itself cannot run here).
+
+The vectors are small (a few hundred KB) so the GPU box, which has no reference
+tree, can check both the oracle and the CUDA path against them.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from catfish_b200 import synth, weights  # noqa: E402
+from oracle import postprocess, ref_infer, tf_graph  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def label_patterns(rng):
+    pats = [
+        [1] * 20 + [0] * 5, [0] * 5 + [1] * 20, [1] * 14 + [0] * 3 + [1] * 15, [1], [0], [1] * 15, [1] * 14,
+        [0, 1] * 40, [1] * 100, [0] * 100, [1] * 15 + [0] + [1] * 15, [0] + [1] * 31 + [0], [1] * 32 + [0] * 32 + [1] * 33,
+        [2] * 20 + [1] * 3 + [0] * 2 + [3] * 16,
+    ]
+    for n in (31, 32, 33, 63, 64, 65, 257, 1000):
+        p = rng.random() * 0.2 + 0.02
+        bits = []
+        cur = 0
+        while len(bits) < n:
+            run = int(rng.geometric(p))
+            bits.extend([cur] * run)
+            cur ^= 1
+        pats.append(bits[:n])
+    return pats
+
+
+def main():
+    ref = ref_infer.load()
+    rng = np.random.default_rng(2026)
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- post-processing vectors from the reference's own functions
+    post = {}
+    pats = label_patterns(rng)
+    post["n_patterns"] = np.array(len(pats))
+    for i, p in enumerate(pats):
+        post["pat%d" % i] = np.array(p, np.int64)
+        post["pat%d_correct_short" % i] = np.asarray(ref.correct_short(list(p)), np.int64)
+        for lab in (1, 0):
+            post["pat%d_hp_label%d" % (i, lab)] = np.array(ref.hp_in_pred(list(p), label=lab), np.int64).reshape(-1, 2)
+        post["pat%d_hp_ext" % i] = np.array(ref.hp_in_pred(list(p), 3, 0), np.int64).reshape(-1, 2)
+    scores = rng.random(500)
+    scores[::7] = 0.5
+    post["scores"] = scores
+    post["scores_labels_0.5"] = np.array(ref.class_from_threshold(scores), np.int64)
+    post["scores_labels_0.9"] = np.array(ref.class_from_threshold(scores, 0.9), np.int64)
+
+    # ---- normalisation vectors (reference's normalize_raw_signal)
+    raws = [synth.synth_read(n, 7000 + n) for n in (1, 2, 3, 34, 35, 36, 70, 1999, 2000)]
+    raws.append(np.array([1, 2, 3, 4], np.int16))
+    raws.append(np.array([-32768, 32767, 0, 5, 5, 9], np.int16))          # wide value range
+    raws.append(np.array([5, 5, 5, 7, 9, 9], np.int16))
+    post["n_raws"] = np.array(len(raws))
+    for i, r in enumerate(raws):
+        post["raw%d" % i] = r
+        with np.errstate(all="ignore"):
+            post["raw%d_norm" % i] = np.asarray(ref.normalize_raw_signal(r, "median"), np.float64)
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **post)
+
+    # ---- forward vectors: shipped ResNetRNN checkpoint, 4 ragged reads
+    w = weights.load_shipped()
+    fw = {}
+    lengths = [700, 1225, 1999, 2000]        # 1225 = 35 * 35: the "extra window" padding case
+    reads = synth.synth_reads(lengths, base_seed=4242)
+    torch_graph = tf_graph.TorchGraph(w)
+    fw["n_reads"] = np.array(len(reads))
+    for i, r in enumerate(reads):
+        norm = ref.normalize_raw_signal(r, "median")
+        x, pad = postprocess.pad_and_window(norm)
+        p64 = tf_graph.forward_np(w, x, np.float64)[:-pad]
+        p32 = torch_graph.infer(x)[:-pad]
+        labels = ref.correct_short(ref.class_from_threshold(p32))
+        hps = ref.hp_in_pred(labels)
+        fw["read%d" % i] = r
+        fw["read%d_p64" % i] = p64
+        fw["read%d_p32" % i] = p32.astype(np.float32)
+        fw["read%d_hps" % i] = np.array(hps, np.int64).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "forward_resnetrnn_shipped.npz"), **fw)
+
+    # ---- forward vectors: random-init RNN-only and ResNet-only (A14), 48 windows
+    for kind, hpm, seed in (("RNN", dict(layer_size=64, n_layers=3), 11),
+                            ("ResNet", dict(layer_size_res=32, n_layers_res=2), 12),
+                            ("RNN", dict(layer_size=16, n_layers=2), 13)):
+        wr = weights.random_init(kind, seed=seed, **hpm)
+        x = rng.normal(0, 1.5, size=(48, 35, 1)).astype(np.float32)
+        p64 = tf_graph.forward_np(wr, x, np.float64)
+        tag = "%s_%s" % (kind.lower(), "_".join("%s%d" % (k[0] + k[-1], v) for k, v in sorted(hpm.items())))
+        np.savez_compressed(os.path.join(OUT, "forward_%s_seed%d.npz" % (tag, seed)),
+                            x=x, p64=p64, seed=np.array(seed), kind=np.array(kind),
+                            **{"hpm_" + k: np.array(v) for k, v in hpm.items()})
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
