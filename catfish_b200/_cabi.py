@@ -61,6 +61,10 @@ SIGNATURES = {
     "cf_correct_short": (ctypes.c_int, [ctypes.c_int32, c_void, ctypes.c_int64, ctypes.c_int32, c_void, c_void]),
     "cf_hp_in_pred": (ctypes.c_int, [ctypes.c_int32, c_void, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                      ctypes.c_int64, c_void, ctypes.c_int64, c_void, c_void]),
+    "cf_profile_enable": (ctypes.c_int, [c_void, ctypes.c_int32]),
+    "cf_profile_num_classes": (ctypes.c_int, []),
+    "cf_profile_class_name": (ctypes.c_char_p, [ctypes.c_int32]),
+    "cf_profile_read": (ctypes.c_int, [c_void, ctypes.POINTER(ctypes.c_double), c_i64_p, ctypes.c_int32]),
     "cf_launch_count": (ctypes.c_int64, []),
 }
 
@@ -110,3 +114,17 @@ def check(status):
 
 def launch_count():
     return int(load_library().cf_launch_count())
+
+
+def profile_enable(model_handle, on=True):
+    check(load_library().cf_profile_enable(model_handle, 1 if on else 0))
+
+
+def profile_read(model_handle):
+    """{kernel_class: (milliseconds, launches)} accumulated since profile_enable."""
+    lib = load_library()
+    n = lib.cf_profile_num_classes()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(lib.cf_profile_read(model_handle, ms, cnt, n))
+    return {lib.cf_profile_class_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}

@@ -37,6 +37,38 @@ int DevBuf::ensure(size_t want) {
     bytes = grow;
     return CF_OK;
 }
+const char* kernel_class_name(int cls) {
+    static const char* names[KC_COUNT] = {"k1_stats", "k1_window_table", "k2_conv_stack", "k3_gru_input_proj",
+                                          "k4_gru_recurrence", "k5_head", "k6_intervals"};
+    return cls >= 0 && cls < KC_COUNT ? names[cls] : "?";
+}
+
+cudaEvent_t Profiler::get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void Profiler::collect() {
+    for (Rec& r : recs) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.cls] += t;
+        pool.push_back(r.a);
+        pool.push_back(r.b);
+    }
+    recs.clear();
+    cudaGetLastError();
+}
+void Profiler::reset() {
+    collect();
+    for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; }
+}
+void Profiler::release() {
+    collect();
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+}
+
 void DevBuf::release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
 
 int HostBuf::ensure(size_t want) {
@@ -214,6 +246,7 @@ struct cf_model {
     cf::DevBuf tab_src, tab_valid, tab_read;
     cf::DevBuf probs_internal;
     cf::IntervalScratch k6;
+    cf::Profiler prof;
     // host-buffer entry point
     cf::DevBuf h_raw, h_intervals, h_ioff, h_probs;
     cf::HostBuf pin_io;
@@ -244,8 +277,8 @@ static int use_device(int device) {
 static int engine_forward(cf_model* m, const int16_t* raw, const double* stats, const float* xwin,
                           WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream) {
     if (m->engine == CF_ENGINE_TCGEN05)
-        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream);
-    return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream);
+        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof);
+    return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof);
 }
 
 // Validate offsets and lay out the windows of every read (infer.py:32-43).
@@ -330,13 +363,22 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
         CF_TRY(m->probs_internal.ensure(sizeof(float) * (size_t)plan.total_samples));
         probs = m->probs_internal.as<float>();
     }
-    CF_TRY(k1_read_stats(raw0, offsets_dev, n_reads, m->stats.as<double>(), m->wide_flags.as<int32_t>(),
-                         m->wide_scratch.as<uint32_t>(), kWideSlots, stream));
-    CF_TRY(k1_window_table(offsets_dev, win_off_dev, n_reads, plan.total_windows, plan.n_tiles, tab, stream));
+    {
+        ProfScope ps(&m->prof, KC_K1_STATS, stream, 2);
+        CF_TRY(k1_read_stats(raw0, offsets_dev, n_reads, m->stats.as<double>(), m->wide_flags.as<int32_t>(),
+                             m->wide_scratch.as<uint32_t>(), kWideSlots, stream));
+    }
+    {
+        ProfScope ps(&m->prof, KC_K1_TABLE, stream);
+        CF_TRY(k1_window_table(offsets_dev, win_off_dev, n_reads, plan.total_windows, plan.n_tiles, tab, stream));
+    }
     CF_TRY(engine_forward(m, raw0, m->stats.as<double>(), nullptr, tab, plan.n_tiles, probs, stream));
-    CF_TRY(k6_call_intervals(m->k6, probs, BITS_FROM_F32, threshold, 1, offsets_dev, n_reads,
-                             plan.total_samples, intervals_dev, interval_offsets_dev, nullptr, capacity,
-                             min_run, ext_left, ext_right, stream));
+    {
+        ProfScope ps(&m->prof, KC_K6_INTERVALS, stream, 6);
+        CF_TRY(k6_call_intervals(m->k6, probs, BITS_FROM_F32, threshold, 1, offsets_dev, n_reads,
+                                 plan.total_samples, intervals_dev, interval_offsets_dev, nullptr, capacity,
+                                 min_run, ext_left, ext_right, stream));
+    }
     return CF_OK;
 }
 
@@ -422,11 +464,33 @@ void cf_model_destroy(cf_model* m) {
     m->k6.bits.release(); m->k6.block_cnt.release(); m->k6.read_cnt.release(); m->k6.misc.release();
     m->h_raw.release(); m->h_intervals.release(); m->h_ioff.release(); m->h_probs.release();
     m->pin_io.release();
+    m->prof.release();
     if (m->plan_copied) cudaEventDestroy(m->plan_copied);
     delete m;
 }
 
 int cf_model_engine(const cf_model* m) { return m ? m->engine : CF_ERR_BAD_ARG; }
+
+int cf_profile_enable(cf_model* m, int32_t on) {
+    if (!m) { cf::set_error("cf_profile_enable: NULL model"); return CF_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    cudaSetDevice(m->device);
+    m->prof.reset();
+    m->prof.on = on != 0;
+    return CF_OK;
+}
+
+int cf_profile_num_classes(void) { return cf::KC_COUNT; }
+const char* cf_profile_class_name(int32_t cls) { return cf::kernel_class_name(cls); }
+
+int cf_profile_read(cf_model* m, double* ms_out, int64_t* launches_out, int32_t n) {
+    if (!m || !ms_out || !launches_out || n < cf::KC_COUNT) { cf::set_error("cf_profile_read: bad argument"); return CF_ERR_BAD_ARG; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    cudaSetDevice(m->device);
+    m->prof.collect();
+    for (int i = 0; i < cf::KC_COUNT; ++i) { ms_out[i] = m->prof.ms[i]; launches_out[i] = m->prof.launches[i]; }
+    return CF_OK;
+}
 
 int cf_model_reserve(cf_model* m, int64_t max_samples, int32_t max_reads) {
     if (!m || max_samples < 0 || max_reads < 0) { cf::set_error("cf_model_reserve: bad argument"); return CF_ERR_BAD_ARG; }

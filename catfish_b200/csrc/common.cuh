@@ -51,6 +51,48 @@ extern std::atomic<long long> g_launches;
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
+// ---------------------------------------------------------------- per-kernel-class timing
+// Optional CUDA-event brackets around every launch, grouped by kernel class, so that bench.py can
+// report the dominant kernel's duration measured on the launching stream.
+enum KernelClass {
+    KC_K1_STATS = 0,   // median / MAD
+    KC_K1_TABLE,       // window table
+    KC_K2_CONV,        // residual conv stack (incl. normalise + window gather)
+    KC_K3_XPROJ,       // GRU input projection GEMM
+    KC_K4_GRU,         // GRU recurrence
+    KC_K5_HEAD,        // dense + sigmoid + un-window
+    KC_K6_INTERVALS,   // threshold / run-length / interval emission
+    KC_COUNT
+};
+const char* kernel_class_name(int cls);
+
+struct Profiler {
+    bool on = false;
+    struct Rec { int cls; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[KC_COUNT] = {};
+    long long launches[KC_COUNT] = {};
+    cudaEvent_t get();
+    void collect();          // synchronises on the recorded events and folds them into ms[]
+    void reset();
+    void release();
+};
+
+// RAII bracket: records an event pair around the launches issued in its scope.
+struct ProfScope {
+    Profiler* p; cudaStream_t s; cudaEvent_t b = nullptr;
+    ProfScope(Profiler* prof, int cls, cudaStream_t stream, int n_launches = 1) : p(prof), s(stream) {
+        if (!p || !p->on) { p = nullptr; return; }
+        cudaEvent_t a = p->get();
+        b = p->get();
+        cudaEventRecord(a, s);
+        p->recs.push_back({cls, a, b});
+        p->launches[cls] += n_launches;
+    }
+    ~ProfScope() { if (p) cudaEventRecord(b, s); }
+};
+
 // ---------------------------------------------------------------- device buffers
 // A growable device allocation owned by a handle; grows only when asked for more.
 struct DevBuf {

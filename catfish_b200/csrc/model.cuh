@@ -54,7 +54,7 @@ void simt_destroy(SimtEngine* e);
 // scattered to probs[tab.src[g] + t] for t < tab.valid[g].
 int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                  const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-                 cudaStream_t stream);
+                 cudaStream_t stream, Profiler* prof);
 size_t simt_workspace_bytes(const HostModel& hm, int64_t n_tiles);
 
 // ---------------------------------------------------------------- tcgen05 engine
@@ -64,6 +64,6 @@ TcEngine* tc_create(const HostModel& hm);
 void tc_destroy(TcEngine* e);
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-               cudaStream_t stream);
+               cudaStream_t stream, Profiler* prof);
 
 }  // namespace cf

@@ -280,7 +280,7 @@ size_t simt_workspace_bytes(const HostModel& hm, int64_t n_tiles) {
 
 int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                  const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, Profiler* prof) {
     if (n_tiles <= 0) return CF_OK;
     CF_TRY(e->ws.ensure(simt_workspace_bytes(hm, n_tiles)));
     const int C = hm.conv_channels(), H = hm.desc.layer_size;
@@ -297,15 +297,19 @@ int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const d
     for (int64_t tile0 = 0; tile0 < n_tiles; tile0 += kSimtChunkTiles) {
         const int64_t tiles = (n_tiles - tile0) < kSimtChunkTiles ? (n_tiles - tile0) : kSimtChunkTiles;
         const int64_t rows = tiles * kWindow * kTileWindows;
-        simt_fill_x_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
-            raw, stats, xwin, tab.src, tab.valid, tab.read, tile0, rows, x);
-        CF_LAUNCHED();
+        {
+            ProfScope ps(prof, KC_K2_CONV, stream);
+            simt_fill_x_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
+                raw, stats, xwin, tab.src, tab.valid, tab.read, tile0, rows, x);
+            CF_LAUNCHED();
+        }
         const float* feat = x;
         int feat_dim = 1;
         for (int b = 0; b < hm.n_res(); ++b) {
             auto conv = [&](int i, const float* in, const float* res, float* out, int relu) -> int {
                 const ConvLayer& c = hm.convs[i];
                 const int64_t total = rows * c.cout;
+                ProfScope ps(prof, KC_K2_CONV, stream);
                 simt_conv_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
                     in, e->conv_w[i], e->conv_b[i], res, out, rows, c.k, c.cin, c.cout, relu);
                 CF_LAUNCHED();
@@ -324,16 +328,23 @@ int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const d
             const int in_dim = l == 0 ? feat_dim : 2 * H;
             const float* a = l == 0 ? feat : yin;
             dim3 grid((unsigned)ceil_div(rows, 64), (unsigned)ceil_div(6 * H, 64));
-            simt_gemm_bias_kernel<<<grid, 256, 0, stream>>>(a, e->gru_wx[l], e->gru_bx[l], xproj, rows, 6 * H, in_dim);
-            CF_LAUNCHED();
+            {
+                ProfScope ps(prof, KC_K3_XPROJ, stream);
+                simt_gemm_bias_kernel<<<grid, 256, 0, stream>>>(a, e->gru_wx[l], e->gru_bx[l], xproj, rows, 6 * H, in_dim);
+                CF_LAUNCHED();
+            }
             float* yout = (l & 1) ? y1 : y0;
             const size_t smem = sizeof(float) * 2 * 32 * (H + 1);
-            simt_gru_kernel<<<dim3((unsigned)tiles, 4, 2), 256, smem, stream>>>(
-                xproj, e->gru_wgh[2 * l], e->gru_wch[2 * l], e->gru_wgh[2 * l + 1], e->gru_wch[2 * l + 1], yout, H);
-            CF_LAUNCHED();
+            {
+                ProfScope ps(prof, KC_K4_GRU, stream);
+                simt_gru_kernel<<<dim3((unsigned)tiles, 4, 2), 256, smem, stream>>>(
+                    xproj, e->gru_wgh[2 * l], e->gru_wch[2 * l], e->gru_wgh[2 * l + 1], e->gru_wch[2 * l + 1], yout, H);
+                CF_LAUNCHED();
+            }
             yin = yout;
         }
         const float* hin = hm.n_rnn() ? yin : feat;
+        ProfScope ps(prof, KC_K5_HEAD, stream);
         simt_head_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
             hin, e->head_w, e->head_b, hm.head_features(), tab.src, tab.valid, tab.read, raw ? stats : nullptr,
             tile0, rows, probs);

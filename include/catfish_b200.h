@@ -175,6 +175,17 @@ int cf_hp_in_pred(int32_t device, const int64_t* labels_dev, int64_t n, int32_t 
                   int32_t ext_right, int64_t label, int64_t* intervals_dev, int64_t capacity,
                   int64_t* n_out_dev, void* stream);
 
+/*
+ * Per-kernel-class device timing (no reference counterpart; used by bench.py for the roofline).
+ * When enabled, every launch group is bracketed by CUDA events on the launching stream;
+ * cf_profile_read waits for them and returns accumulated milliseconds and launch counts per
+ * class (arrays of at least cf_profile_num_classes() elements).  Enabling resets the counters.
+ */
+int cf_profile_enable(cf_model* model, int32_t on);
+int cf_profile_num_classes(void);
+const char* cf_profile_class_name(int32_t cls);
+int cf_profile_read(cf_model* model, double* ms_out, int64_t* launches_out, int32_t n);
+
 /* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t cf_launch_count(void);
 

@@ -1,0 +1,128 @@
+"""GPU: network forward and the end-to-end per-read entry points against the oracle.
+
+Contract (BASELINE.json north_star): probabilities within 1e-3 absolute of the
+reference's fp32 CPU path; interval calls identical except where the reference
+probability lies within 1e-3 of the threshold."""
+import numpy as np
+import pytest
+
+from helpers import allowed_label_flips, golden, hpm_from_golden
+from catfish_b200 import infer, neural_network, synth, weights
+from oracle import postprocess, tf_graph
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3          # north_star tolerance
+ENGINES = ["simt", "auto"]
+
+
+def _model(kind, engine, w=None, **hpm):
+    full = dict(weights.SHIPPED_HPARAMS)
+    full.update(hpm)
+    m = neural_network.build_model(kind, engine=engine, **full)
+    m.set_weights(w if w is not None else weights.load_shipped())
+    return m
+
+
+def _check_intervals(got_hps, scores_gpu, p_ref, threshold=0.5):
+    """Intervals must equal the oracle's; where they differ, every differing label must sit in the
+    allowed band, and the GPU intervals must be the exact post-processing of the GPU labels."""
+    ref_labels = postprocess.class_from_threshold(p_ref, threshold)
+    want = postprocess.hp_in_pred(postprocess.correct_short(ref_labels))
+    if got_hps == want:
+        return
+    gpu_labels = postprocess.class_from_threshold(scores_gpu.astype(np.float64), threshold)
+    diff = gpu_labels != ref_labels
+    assert diff.any() and np.all(allowed_label_flips(p_ref, threshold)[diff]), "interval mismatch outside the band"
+    assert got_hps == postprocess.hp_in_pred(postprocess.correct_short(gpu_labels))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_infer_windows_shipped_vs_oracle(engine, shipped_weights):
+    rng = np.random.default_rng(0)
+    m = _model("ResNetRNN", engine)
+    graph = tf_graph.TorchGraph(shipped_weights)
+    for n_windows in (1, 127, 128, 129, 300):
+        x = rng.normal(0, 1.5, size=(n_windows, 35, 1)).astype(np.float32)
+        got = m.infer(x)
+        assert got.dtype == np.float64 and got.shape == (n_windows * 35,)
+        assert np.abs(got - graph.infer(x)).max() < PROB_TOL
+    with pytest.raises(ValueError):
+        m.infer(np.zeros((3, 34, 1)))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["forward_rnn_le64_ns3_seed11.npz", "forward_resnet_ls32_ns2_seed12.npz",
+                                  "forward_rnn_le16_ns2_seed13.npz"])
+def test_variants_random_init_vs_golden(engine, name):
+    g = golden(name)
+    hpm = hpm_from_golden(g)
+    kind = str(g["kind"])
+    w = weights.random_init(kind, seed=int(g["seed"]), **hpm)
+    m = _model(kind, engine, w, **hpm)
+    got = m.infer(g["x"])
+    assert np.abs(got - g["p64"]).max() < PROB_TOL
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reads_golden_shipped(engine):
+    g = golden("forward_resnetrnn_shipped.npz")
+    m = _model("ResNetRNN", engine)
+    reads = [g["read%d" % i] for i in range(int(g["n_reads"]))]
+    hps, lengths, scores = infer.infer_reads(reads, m, return_scores=True)
+    for i, r in enumerate(reads):
+        assert lengths[i] == len(r)
+        assert scores[i].shape == (len(r),)
+        assert np.abs(scores[i] - g["read%d_p32" % i]).max() < PROB_TOL
+        _check_intervals(hps[i], scores[i], g["read%d_p32" % i].astype(np.float64))
+        for a, b in hps[i]:
+            assert isinstance(a, int) and isinstance(b, int)
+    # single-read entry point returns the same as the batch
+    one_hps, one_len = infer.infer_class_from_raw(reads[1], m)
+    assert one_hps == hps[1] and one_len == lengths[1]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reads_ragged_vs_oracle(engine, shipped_weights):
+    """Config-1 style: synthetic reads of ragged lengths incl. the padding edge cases."""
+    lengths = [35, 36, 69, 70, 71, 4480, 4481, 10000, 10000, 12345, 1, 34]
+    reads = synth.synth_reads(lengths, base_seed=300)
+    m = _model("ResNetRNN", engine)
+    graph = tf_graph.TorchGraph(shipped_weights)
+    hps, lens, scores = infer.infer_reads(reads, m, return_scores=True)
+    worst = 0.0
+    for i, r in enumerate(reads):
+        want_hps, want_len, want_scores = postprocess.infer_read(r, graph.infer)
+        assert lens[i] == want_len
+        worst = max(worst, float(np.abs(scores[i] - want_scores).max()))
+        _check_intervals(hps[i], scores[i], want_scores)
+    assert worst < PROB_TOL, worst
+
+
+def test_degenerate_and_error_cases():
+    m = _model("ResNetRNN", "auto")
+    with pytest.raises(IndexError):
+        infer.infer_reads([np.zeros(0, np.int16)], m)
+    const = np.full(200, 512, np.int16)                   # MAD = 0: the reference divides by zero -> NaN
+    hps, lens, scores = infer.infer_reads([const, synth.synth_read(500, 1)], m, return_scores=True)
+    assert hps[0] == [] and lens == [200, 500] and np.all(np.isnan(scores[0]))
+    assert np.all(np.isfinite(scores[1]))
+    with pytest.raises(ValueError):
+        infer.infer_class_from_signal("/nonexistent/file.fast5", m)
+    assert infer.infer_reads([], m) == ([], [])
+
+
+def test_engine_cross_check_large():
+    """tcgen05 engine vs the fp32 SIMT engine on a batch the CPU oracle would take minutes for."""
+    fast = _model("ResNetRNN", "auto")
+    if fast.resolved_engine == "simt":
+        pytest.skip("tcgen05 engine not available for this build")
+    slow = _model("ResNetRNN", "simt")
+    reads = synth.synth_reads(synth.ragged_lengths(40, 20000, 60000, seed=5), base_seed=900)
+    h1, l1, s1 = infer.infer_reads(reads, fast, return_scores=True)
+    h2, l2, s2 = infer.infer_reads(reads, slow, return_scores=True)
+    assert l1 == l2
+    worst = max(float(np.abs(a - b).max()) for a, b in zip(s1, s2))
+    assert worst < PROB_TOL, worst
+    for a, b, sa, sb in zip(h1, h2, s1, s2):
+        _check_intervals(a, sa, sb.astype(np.float64))
