@@ -10,6 +10,8 @@
 
 namespace cf {
 
+static int use_device(int device);
+
 // ---------------------------------------------------------------- errors / counters
 static thread_local std::string t_error;
 std::atomic<long long> g_launches{0};
@@ -394,6 +396,13 @@ int cf_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int32_t k, const float* wx_host,
+                      const float* bias_host, float* out_dev, void* stream) {
+    if (!a_dev || !wx_host || !bias_host || !out_dev || n_blocks <= 0) { cf::set_error("cf_selftest_xproj: bad argument"); return CF_ERR_BAD_ARG; }
+    CF_TRY(cf::use_device(device));
+    return cf::tc_selftest_xproj(a_dev, n_blocks, k, wx_host, bias_host, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int64_t cf_launch_count(void) { return (int64_t)cf::g_launches.load(); }

@@ -55,7 +55,6 @@ void simt_destroy(SimtEngine* e);
 int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                  const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
                  cudaStream_t stream, Profiler* prof);
-size_t simt_workspace_bytes(const HostModel& hm, int64_t n_tiles);
 
 // ---------------------------------------------------------------- tcgen05 engine
 struct TcEngine;
@@ -65,5 +64,8 @@ void tc_destroy(TcEngine* e);
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
                cudaStream_t stream, Profiler* prof);
+
+int tc_selftest_xproj(const float* a_dev, int64_t n_blocks, int K, const float* wx_host, const float* bias_host,
+                      float* out_dev, cudaStream_t stream);
 
 }  // namespace cf

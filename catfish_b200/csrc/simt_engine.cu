@@ -268,61 +268,83 @@ __global__ void simt_head_kernel(const float* __restrict__ y, const float* __res
 }
 
 // ---------------------------------------------------------------- forward
-size_t simt_workspace_bytes(const HostModel& hm, int64_t n_tiles) {
-    const int64_t tiles = n_tiles < kSimtChunkTiles ? n_tiles : kSimtChunkTiles;
-    const int64_t rows = tiles * kWindow * kTileWindows;
+// Carve the workspace for passes of at most `chunk_tiles` tiles.
+struct SimtBufs { float *x, *ca, *cb, *csc, *cout, *xproj, *y0, *y1; };
+
+static int simt_prepare(SimtEngine* e, const HostModel& hm, int64_t chunk_tiles, bool with_rnn, SimtBufs* b) {
+    const int64_t rows = chunk_tiles * kWindow * kTileWindows;
     const int C = hm.conv_channels(), H = hm.desc.layer_size;
-    size_t fl = (size_t)rows;                                  // x
-    if (hm.n_res()) fl += (size_t)rows * C * 4;                // a, b, sc, out
-    if (hm.n_rnn()) fl += (size_t)rows * (6 * H + 2 * 2 * H);  // xproj + y ping-pong
-    return fl * sizeof(float) + 1024;
+    const bool res = hm.n_res() > 0, rnn = with_rnn && hm.n_rnn() > 0;
+    size_t fl = (size_t)rows;
+    if (res) fl += (size_t)rows * C * 4;
+    if (rnn) fl += (size_t)rows * (6 * H + 2 * 2 * H);
+    CF_TRY(e->ws.ensure(fl * sizeof(float) + 1024));
+    b->x = e->ws.as<float>();
+    b->ca = b->x + rows;
+    b->cb = b->ca + (res ? rows * C : 0);
+    b->csc = b->cb + (res ? rows * C : 0);
+    b->cout = b->csc + (res ? rows * C : 0);
+    b->xproj = b->cout + (res ? rows * C : 0);
+    b->y0 = b->xproj + (rnn ? rows * 6 * H : 0);
+    b->y1 = b->y0 + (rnn ? rows * 2 * H : 0);
+    return CF_OK;
+}
+
+// Normalise + window gather + residual blocks for tiles [tile0, tile0 + tiles): *feat points at
+// fp32 rows [(tile*35+t)*128+w][C] (or [..][1] when the network has no residual blocks).
+static int conv_stack(SimtEngine* e, const HostModel& hm, const SimtBufs& b, const int16_t* raw, const double* stats,
+                      const float* xwin, WindowTable tab, int64_t tile0, int64_t tiles, const float** feat,
+                      cudaStream_t stream, Profiler* prof) {
+    const int64_t rows = tiles * kWindow * kTileWindows;
+    {
+        ProfScope ps(prof, KC_K2_CONV, stream);
+        simt_fill_x_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
+            raw, stats, xwin, tab.src, tab.valid, tab.read, tile0, rows, b.x);
+        CF_LAUNCHED();
+    }
+    *feat = b.x;
+    for (int blk = 0; blk < hm.n_res(); ++blk) {
+        auto conv = [&](int i, const float* in, const float* res, float* out, int relu) -> int {
+            const ConvLayer& c = hm.convs[i];
+            const int64_t total = rows * c.cout;
+            ProfScope ps(prof, KC_K2_CONV, stream);
+            simt_conv_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
+                in, e->conv_w[i], e->conv_b[i], res, out, rows, c.k, c.cin, c.cout, relu);
+            CF_LAUNCHED();
+            return CF_OK;
+        };
+        const int i = 4 * blk;
+        CF_TRY(conv(i, *feat, nullptr, b.csc, 0));          // shortcut: BN(conv k1)
+        CF_TRY(conv(i + 1, *feat, nullptr, b.ca, 1));
+        CF_TRY(conv(i + 2, b.ca, nullptr, b.cb, 1));
+        CF_TRY(conv(i + 3, b.cb, b.csc, b.cout, 1));        // relu(relu(BN(conv)) + shortcut)
+        *feat = b.cout;                                     // conv i+3 no longer reads the block input
+    }
+    return CF_OK;
+}
+
+int simt_conv_stack(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats, const float* xwin,
+                    WindowTable tab, int64_t tile0, int64_t tiles, int64_t chunk_tiles, const float** feat,
+                    cudaStream_t stream, Profiler* prof) {
+    SimtBufs b;
+    CF_TRY(simt_prepare(e, hm, chunk_tiles, false, &b));
+    return conv_stack(e, hm, b, raw, stats, xwin, tab, tile0, tiles, feat, stream, prof);
 }
 
 int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                  const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
                  cudaStream_t stream, Profiler* prof) {
     if (n_tiles <= 0) return CF_OK;
-    CF_TRY(e->ws.ensure(simt_workspace_bytes(hm, n_tiles)));
-    const int C = hm.conv_channels(), H = hm.desc.layer_size;
-    const int64_t chunk_rows_max = (n_tiles < kSimtChunkTiles ? n_tiles : kSimtChunkTiles) * kWindow * kTileWindows;
-    float* x = e->ws.as<float>();
-    float* ca = x + chunk_rows_max;
-    float* cb = ca + (hm.n_res() ? chunk_rows_max * C : 0);
-    float* csc = cb + (hm.n_res() ? chunk_rows_max * C : 0);
-    float* cout = csc + (hm.n_res() ? chunk_rows_max * C : 0);
-    float* xproj = cout + (hm.n_res() ? chunk_rows_max * C : 0);
-    float* y0 = xproj + (hm.n_rnn() ? chunk_rows_max * 6 * H : 0);
-    float* y1 = y0 + (hm.n_rnn() ? chunk_rows_max * 2 * H : 0);
-
+    const int64_t chunk = n_tiles < kSimtChunkTiles ? n_tiles : kSimtChunkTiles;
+    SimtBufs b;
+    CF_TRY(simt_prepare(e, hm, chunk, true, &b));
+    const int H = hm.desc.layer_size;
     for (int64_t tile0 = 0; tile0 < n_tiles; tile0 += kSimtChunkTiles) {
         const int64_t tiles = (n_tiles - tile0) < kSimtChunkTiles ? (n_tiles - tile0) : kSimtChunkTiles;
         const int64_t rows = tiles * kWindow * kTileWindows;
-        {
-            ProfScope ps(prof, KC_K2_CONV, stream);
-            simt_fill_x_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
-                raw, stats, xwin, tab.src, tab.valid, tab.read, tile0, rows, x);
-            CF_LAUNCHED();
-        }
-        const float* feat = x;
-        int feat_dim = 1;
-        for (int b = 0; b < hm.n_res(); ++b) {
-            auto conv = [&](int i, const float* in, const float* res, float* out, int relu) -> int {
-                const ConvLayer& c = hm.convs[i];
-                const int64_t total = rows * c.cout;
-                ProfScope ps(prof, KC_K2_CONV, stream);
-                simt_conv_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(
-                    in, e->conv_w[i], e->conv_b[i], res, out, rows, c.k, c.cin, c.cout, relu);
-                CF_LAUNCHED();
-                return CF_OK;
-            };
-            const int i = 4 * b;
-            CF_TRY(conv(i, feat, nullptr, csc, 0));          // shortcut: BN(conv k1)
-            CF_TRY(conv(i + 1, feat, nullptr, ca, 1));
-            CF_TRY(conv(i + 2, ca, nullptr, cb, 1));
-            CF_TRY(conv(i + 3, cb, csc, cout, 1));           // relu(relu(BN(conv)) + shortcut)
-            feat = cout;                                     // conv i+3 no longer reads the block input
-            feat_dim = C;
-        }
+        const float* feat = nullptr;
+        CF_TRY(conv_stack(e, hm, b, raw, stats, xwin, tab, tile0, tiles, &feat, stream, prof));
+        const int feat_dim = hm.n_res() ? hm.conv_channels() : 1;
         float* yin = nullptr;
         for (int l = 0; l < hm.n_rnn(); ++l) {
             const int in_dim = l == 0 ? feat_dim : 2 * H;
@@ -330,15 +352,15 @@ int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const d
             dim3 grid((unsigned)ceil_div(rows, 64), (unsigned)ceil_div(6 * H, 64));
             {
                 ProfScope ps(prof, KC_K3_XPROJ, stream);
-                simt_gemm_bias_kernel<<<grid, 256, 0, stream>>>(a, e->gru_wx[l], e->gru_bx[l], xproj, rows, 6 * H, in_dim);
+                simt_gemm_bias_kernel<<<grid, 256, 0, stream>>>(a, e->gru_wx[l], e->gru_bx[l], b.xproj, rows, 6 * H, in_dim);
                 CF_LAUNCHED();
             }
-            float* yout = (l & 1) ? y1 : y0;
+            float* yout = (l & 1) ? b.y1 : b.y0;
             const size_t smem = sizeof(float) * 2 * 32 * (H + 1);
             {
                 ProfScope ps(prof, KC_K4_GRU, stream);
                 simt_gru_kernel<<<dim3((unsigned)tiles, 4, 2), 256, smem, stream>>>(
-                    xproj, e->gru_wgh[2 * l], e->gru_wch[2 * l], e->gru_wgh[2 * l + 1], e->gru_wch[2 * l + 1], yout, H);
+                    b.xproj, e->gru_wgh[2 * l], e->gru_wch[2 * l], e->gru_wgh[2 * l + 1], e->gru_wch[2 * l + 1], yout, H);
                 CF_LAUNCHED();
             }
             yin = yout;

@@ -186,6 +186,16 @@ int cf_profile_num_classes(void);
 const char* cf_profile_class_name(int32_t cls);
 int cf_profile_read(cf_model* model, double* ms_out, int64_t* launches_out, int32_t n);
 
+/*
+ * cf_selftest_xproj - unit self-test of the tcgen05 GEMM path (no reference counterpart): the GRU
+ * input projection out[blk][n][w] = sum_k a[blk*128 + w][k] * wx[k][n] + bias[n], n in [0, 384),
+ * through the engine's operand packing, bulk (TMA) copies, tcgen05.mma and TMEM epilogue.
+ * a_dev float32 [n_blocks*128][k] (device), wx_host [k][384], bias_host [384] (host),
+ * out_dev float32 [n_blocks][384][128] (device); k is 32 or 128.  Synchronises.
+ */
+int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int32_t k, const float* wx_host,
+                      const float* bias_host, float* out_dev, void* stream);
+
 /* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t cf_launch_count(void);
 
