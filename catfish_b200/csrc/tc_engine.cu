@@ -33,6 +33,16 @@ constexpr int kC = 32;            // conv channels
 constexpr int kNX = 3 * kH;       // 192 projection columns per direction (r | u | c)
 constexpr int kTcChunkTiles = 592;   // tiles per internal pass (4 waves of 148 CTAs)
 
+struct ConvParams {                    // byte offsets inside the parameter block
+    static constexpr int kFloats = 10 * 32;              // a_sc b_sc a1 b1 | b2 b3 b4 b5 b6 b7
+    static constexpr int kW2 = kFloats * 4;              // 3 taps x {hi, lo} x [4][32][8]
+    static constexpr int kW3 = kW2 + 3 * 4096;
+    static constexpr int kW45 = kW3 + 4096;              // {hi, lo} x [4][64][8]
+    static constexpr int kW6 = kW45 + 8192;
+    static constexpr int kW7 = kW6 + 3 * 4096;
+    static constexpr int kBytes = kW7 + 4096;            // 42240
+};
+
 // ====================================================================== weight packing (host)
 // B operand of D = A * W for W [K][N] row-major: stored [plane][K/8][N][8] with plane 0 = hi.
 static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std::vector<__nv_bfloat16>* out) {
@@ -61,7 +71,9 @@ struct TcLayer {
 };
 
 struct TcEngine {
-    SimtEngine* simt = nullptr;       // conv stack (fp32) until TK2 lands; owns its workspace
+    SimtEngine* simt = nullptr;       // fp32 conv stack for shapes TK2 is not specialised for
+    uint8_t* conv_params = nullptr;   // TK2 parameter block (see ConvParams), nullptr = use simt
+    int conv_nres = 0;
     std::vector<TcLayer> layers;
     float* head_w = nullptr;          // [128]
     float head_b = 0.f;
@@ -93,6 +105,39 @@ TcEngine* tc_create(const HostModel& hm) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, dev);
     e->simt = simt_create(hm);
+    if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
+        // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
+        std::vector<uint8_t> blk(ConvParams::kBytes, 0);
+        float* fp = reinterpret_cast<float*>(blk.data());
+        auto put = [&](int slot, const std::vector<float>& v) { memcpy(fp + 32 * slot, v.data(), 32 * sizeof(float)); };
+        put(0, hm.convs[0].w); put(1, hm.convs[0].b);          // shortcut of block 0: [1][1][32]
+        put(2, hm.convs[1].w); put(3, hm.convs[1].b);
+        put(4, hm.convs[2].b); put(5, hm.convs[3].b);
+        auto put_w = [&](int off, const float* w, int n, int ldw, int col0, int dst_col0, int n_total) {
+            // pack a [32][n] matrix into columns [dst_col0, dst_col0 + n) of a {hi, lo} x [4][n_total][8] operand
+            __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(blk.data() + off);
+            __nv_bfloat16* lo = hi + 32 * n_total;
+            for (int k = 0; k < 32; ++k)
+                for (int j = 0; j < n; ++j) {
+                    const float v = w[(size_t)k * ldw + col0 + j];
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    const size_t idx = ((size_t)(k / 8) * n_total + dst_col0 + j) * 8 + (k % 8);
+                    hi[idx] = h;
+                    lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+        };
+        for (int tap = 0; tap < 3; ++tap) put_w(ConvParams::kW2 + tap * 4096, hm.convs[2].w.data() + tap * 32 * 32, 32, 32, 0, 0, 32);
+        put_w(ConvParams::kW3, hm.convs[3].w.data(), 32, 32, 0, 0, 32);
+        if (hm.n_res() == 2) {
+            put(6, hm.convs[4].b); put(7, hm.convs[5].b); put(8, hm.convs[6].b); put(9, hm.convs[7].b);
+            put_w(ConvParams::kW45, hm.convs[4].w.data(), 32, 32, 0, 0, 64);       // sc1 columns 0..31
+            put_w(ConvParams::kW45, hm.convs[5].w.data(), 32, 32, 0, 32, 64);      // p1 columns 32..63
+            for (int tap = 0; tap < 3; ++tap) put_w(ConvParams::kW6 + tap * 4096, hm.convs[6].w.data() + tap * 32 * 32, 32, 32, 0, 0, 32);
+            put_w(ConvParams::kW7, hm.convs[7].w.data(), 32, 32, 0, 0, 32);
+        }
+        e->conv_params = tc_upload(e, blk);
+        e->conv_nres = hm.n_res();
+    }
     for (int l = 0; l < hm.n_rnn(); ++l) {
         TcLayer L;
         const GruDir& f = hm.gru[2 * l];
@@ -155,6 +200,232 @@ __global__ void tc_pack_a_kernel(const float* __restrict__ in, int K, int64_t n_
     __nv_bfloat16* dst = out + (size_t)blk * 2 * plane + ((size_t)g * 128 + w) * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ====================================================================== TK2: residual conv stack
+// Fuses, per tile of 128 windows: median/MAD normalisation of the raw signal, the 35-sample
+// window gather with zero padding, and the residual blocks of resnet_class.py:44-82 with their
+// batch-norms folded in.  The two Cin = 1 convolutions of block 0 are evaluated in fp32 on CUDA
+// cores from the normalised sample (it is never rounded to bf16); every 32 -> 32 convolution is
+// an implicit GEMM on tcgen05 with split-bf16 operands: rows = the 128 windows of one position
+// t, so the k = 3 taps are whole 128-row operand slices of t-1, t, t+1 and the "same" padding at
+// the window edges is simply a skipped MMA.
+//
+// Time-skewed schedule over u = 0..37 (block-1 stages only when NRES == 2):
+//   phase 1  o1[u]    = relu(x a1 + b1)                     CUDA cores      -> O1[u % 3]
+//   round 1  o2[u-1]  = relu(conv3(o1) + b2)  ;  p2[u-3] = relu(conv3(p1) + b6)
+//   round 2  o3[u-1] -> y0 = relu(relu(o3 + b3) + sc0)  ;  p3[u-3] -> y1 = relu(relu(p3 + b7) + sc1)
+//   round 3  [sc1 | p1][u-1] = y0 [W4 | W5]   (sc1 stays in TMEM until y1 needs it)
+// Each round is: operands to smem -> one thread issues the MMAs -> commit -> all threads run the
+// TMEM epilogue for their own window (thread = TMEM lane = window).
+constexpr uint32_t kSliceBytes = 2u * 128 * kC * 2;       // one position of a tile as A operand: 16 KB
+constexpr uint32_t kConvSmem = ConvParams::kBytes + 9 * kSliceBytes + 35 * 128 * 4 + 256;
+
+__device__ __forceinline__ void store_a_row32(uint8_t* slice, int row, const float* v) {
+    // 32 channels of one window into an operand slice {hi, lo} x [4][128][8]
+#pragma unroll
+    for (int kg = 0; kg < 4; ++kg) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(v[kg * 8 + 2 * i], v[kg * 8 + 2 * i + 1], hi[i], lo[i]);
+        *reinterpret_cast<uint4*>(slice + kg * 2048 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(slice + 8192 + kg * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// 3-pass split-bf16 MMA of one K = 32 operand slice against one [32 x N] weight matrix.
+template <int N>
+__device__ __forceinline__ void conv_mma(uint32_t tmem_d, uint32_t a_slice, uint32_t w_mat, bool first) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, N);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ap = a_slice + (pass == 1 ? 8192u : 0u);
+        const uint32_t wp = w_mat + (pass == 2 ? (uint32_t)(kC * N * 2) : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+            umma_bf16(tmem_d, make_smem_desc(ap + kk * 4096, 2048, 128), make_smem_desc(wp + kk * 2 * (N * 16), N * 16, 128),
+                      idesc, !(first && pass == 0 && kk == 0));
+    }
+}
+
+template <int NRES>
+__global__ void __launch_bounds__(128, 1)
+tc_conv_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
+               const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
+               const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* prm = smem;
+    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 3 slices
+    uint8_t* o2 = o1 + 3 * kSliceBytes;
+    uint8_t* y0 = o2 + kSliceBytes;
+    uint8_t* p1 = y0 + kSliceBytes;                   // ring of 3 slices
+    uint8_t* p2 = p1 + 3 * kSliceBytes;
+    float* xs = reinterpret_cast<float*>(p2 + kSliceBytes);      // [35][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 35 * 128); // 3 round barriers + parameter barrier
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const float* fp = reinterpret_cast<const float*>(prm);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = threadIdx.x;                      // window of the tile = TMEM lane
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bars[3], ConvParams::kBytes);
+        bulk_g2s(prm, params, ConvParams::kBytes, &bars[3]);
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    mbar_wait(&bars[3], 0);
+    const uint32_t prm_u = smem_u32(prm);
+    const uint32_t o1_u = smem_u32(o1), o2_u = smem_u32(o2), y0_u = smem_u32(y0), p1_u = smem_u32(p1), p2_u = smem_u32(p2);
+    // TMEM columns: o2 0, o3 32, [sc1|p1] slots 64 / 128, p2 192, p3 224
+    uint32_t round = 0;                               // completed uses of each round barrier
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- gather + normalise this thread's window (infer.py:101-105, 32-38; f64 -> f32 feed)
+        const int64_t g = (tile0 + tile) * kTileWindows + row;
+        const int nv = valid[g];
+        {
+            const int64_t s0 = src[g];
+            double shift = 0.0, scale = 1.0;
+            if (raw && nv > 0) { const int r = read[g]; shift = stats[2 * r]; scale = stats[2 * r + 1]; }
+            for (int t = 0; t < kWindow; ++t) {
+                float v = 0.f;
+                if (t < nv) v = raw ? (float)(((double)raw[s0 + t] - shift) / scale) : xwin[s0 + t];
+                xs[t * 128 + row] = v;
+            }
+        }
+        const int last_u = NRES == 2 ? kWindow + 2 : kWindow;
+        for (int u = 0; u <= last_u; ++u, ++round) {
+            const int tb = u - 1, tc = u - 3;
+            const bool has_b = tb >= 0 && tb < kWindow;
+            const bool has_c = NRES == 2 && tc >= 0 && tc < kWindow;
+            // ---- phase 1: o1[u] = relu(x a1 + b1)
+            if (u < kWindow) {
+                const float x = xs[u * 128 + row];
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = fmaxf(fmaf(x, fp[64 + c], fp[96 + c]), 0.f);
+                store_a_row32(o1 + (u % 3) * kSliceBytes, row, v);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            // ---- round 1: o2[tb], p2[tc]
+            if (threadIdx.x == 0) {
+                tc_fence_after_sync();
+                if (has_b) {
+                    bool first = true;
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = tb + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma<32>(tmem + 0, o1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first);
+                        first = false;
+                    }
+                }
+                if (has_c) {
+                    bool first = true;
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = tc + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma<32>(tmem + 192, p1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW6 + tap * 4096, first);
+                        first = false;
+                    }
+                }
+                umma_commit(&bars[0]);
+            }
+            mbar_wait(&bars[0], round & 1);
+            tc_fence_after_sync();
+            if (has_b) {
+                float v[32];
+                tmem_ld16(t_lane + 0, v);
+                tmem_ld16(t_lane + 16, v + 16);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + fp[128 + c], 0.f);          // b2
+                store_a_row32(o2, row, v);
+            }
+            if (has_c) {
+                float v[32];
+                tmem_ld16(t_lane + 192, v);
+                tmem_ld16(t_lane + 208, v + 16);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + fp[256 + c], 0.f);          // b6
+                store_a_row32(p2, row, v);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            // ---- round 2: o3[tb], p3[tc]
+            if (threadIdx.x == 0) {
+                tc_fence_after_sync();
+                if (has_b) conv_mma<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true);
+                if (has_c) conv_mma<32>(tmem + 224, p2_u, prm_u + ConvParams::kW7, true);
+                umma_commit(&bars[1]);
+            }
+            mbar_wait(&bars[1], round & 1);
+            tc_fence_after_sync();
+            if (has_b) {
+                float v[32];
+                tmem_ld16(t_lane + 32, v);
+                tmem_ld16(t_lane + 48, v + 16);
+                const float x = xs[tb * 128 + row];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float sc = fmaf(x, fp[c], fp[32 + c]);                           // shortcut BN(conv k1)
+                    v[c] = fmaxf(fmaxf(v[c] + fp[160 + c], 0.f) + sc, 0.f);                 // b3
+                }
+                if (NRES == 2) {
+                    store_a_row32(y0, row, v);
+                } else {
+                    uint8_t* dst = reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + tb) * kSliceBytes;
+                    store_a_row32(dst, row, v);
+                }
+            }
+            if (has_c) {
+                float v[32], sc[32];
+                tmem_ld16(t_lane + 224, v);
+                tmem_ld16(t_lane + 240, v + 16);
+                const uint32_t slot = t_lane + 64 + (tc & 1) * 64;
+                tmem_ld16(slot, sc);
+                tmem_ld16(slot + 16, sc + 16);
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    v[c] = fmaxf(fmaxf(v[c] + fp[288 + c], 0.f) + (sc[c] + fp[192 + c]), 0.f);   // b7, b4
+                uint8_t* dst = reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + tc) * kSliceBytes;
+                store_a_row32(dst, row, v);
+            }
+            if (NRES == 2) {
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                __syncthreads();
+                // ---- round 3: [sc1 | p1][tb] = y0 [W4 | W5]
+                if (threadIdx.x == 0) {
+                    tc_fence_after_sync();
+                    if (has_b) conv_mma<64>(tmem + 64 + (tb & 1) * 64, y0_u, prm_u + ConvParams::kW45, true);
+                    umma_commit(&bars[2]);
+                }
+                mbar_wait(&bars[2], round & 1);
+                tc_fence_after_sync();
+                if (has_b) {
+                    float v[32];
+                    const uint32_t slot = t_lane + 64 + (tb & 1) * 64 + 32;
+                    tmem_ld16(slot, v);
+                    tmem_ld16(slot + 16, v + 16);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + fp[224 + c], 0.f);      // b5
+                    store_a_row32(p1 + (tb % 3) * kSliceBytes, row, v);
+                }
+            }
+        }
+        __syncthreads();          // xs is rewritten by the next tile
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 // ====================================================================== TK3: input projection
@@ -535,6 +806,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
     }
     const int64_t chunk = n_tiles < kTcChunkTiles ? n_tiles : kTcChunkTiles;
@@ -558,8 +831,21 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         const int64_t blocks = tiles * kWindow;
         const int64_t rows = blocks * 128;
         const float* feat = nullptr;             // fp32 rows: conv output [rows][32] or x [rows]
-        CF_TRY(simt_conv_stack(e->simt, hm, raw, stats, xwin, tab, tile0, tiles, chunk, &feat, stream, prof));
         const __nv_bfloat16* a_in = nullptr;
+        if (e->conv_params) {
+            ProfScope ps(prof, KC_K2_CONV, stream);
+            const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
+            if (e->conv_nres == 2)
+                tc_conv_kernel<2><<<grid, 128, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                    tab.read, tile0, (int)tiles, a0);
+            else
+                tc_conv_kernel<1><<<grid, 128, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                    tab.read, tile0, (int)tiles, a0);
+            CF_LAUNCHED();
+            a_in = a0;
+        } else {
+            CF_TRY(simt_conv_stack(e->simt, hm, raw, stats, xwin, tab, tile0, tiles, chunk, &feat, stream, prof));
+        }
         for (int l = 0; l < n_layers; ++l) {
             const TcLayer& L = e->layers[l];
             {
@@ -569,7 +855,7 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     tc_xproj_k1_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(feat, L.wx_f32, L.bx, xp, blocks);
                     CF_LAUNCHED();
                 } else {
-                    if (l == 0) {
+                    if (l == 0 && !a_in) {
                         const int64_t total = rows * (kC / 8);
                         tc_pack_a_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(feat, kC, rows, a0);
                         CF_LAUNCHED();
