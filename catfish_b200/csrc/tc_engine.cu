@@ -647,6 +647,11 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
         }
     } else {
         // ------------------------------------------------------------ epilogue: one window per thread
+        // State h lives in TMEM (fp32, columns 192..255 of the chain's half) next to the
+        // accumulators; registers hold a rolling prefetch P[64] of the xp addends so that every
+        // global load is issued one phase (>= 1000 cycles) before its use:
+        //   while r is computed from P = xp_r, P is refilled with xp_u; during u with xp_c;
+        //   during c with the next step's xp_r.
         const int chain = warp >> 2;                     // 0 forward, 1 backward
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -657,37 +662,61 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
         uint8_t* a_hi = a_s + (size_t)chain * kGruABytes + row * 16;      // + (k/8) * 2048
         uint8_t* a_lo = a_hi + 128 * kH * 2;
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + chain * 256;
-        const uint32_t t_r = t_lane, t_u = t_lane + kH, t_c = t_lane + 2 * kH;
-        float h[kH];
+        const uint32_t t_r = t_lane, t_u = t_lane + kH, t_c = t_lane + 2 * kH, t_h = t_lane + 3 * kH;
+        const float* xp_row = xp + (size_t)chain * kNX * 128 + row;       // + blk * 384 * 128 + col * 128
+        auto blk_of = [&](int tile, int s) -> size_t { return (size_t)tile * kWindow + (chain ? kWindow - 1 - s : s); };
+        float P[kH];
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            {
+                float z[16];
 #pragma unroll
-            for (int j = 0; j < kH; ++j) h[j] = 0.f;
+                for (int i = 0; i < 16; ++i) z[i] = 0.f;
 #pragma unroll
-            for (int kg = 0; kg < kH / 8; ++kg) {
-                *reinterpret_cast<uint4*>(a_hi + kg * 2048) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(a_lo + kg * 2048) = make_uint4(0, 0, 0, 0);
+                for (int c0 = 0; c0 < kH; c0 += 16) tmem_st16(t_h + c0, z);
+#pragma unroll
+                for (int kg = 0; kg < kH / 8; ++kg) {
+                    *reinterpret_cast<uint4*>(a_hi + kg * 2048) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(a_lo + kg * 2048) = make_uint4(0, 0, 0, 0);
+                }
+                if (tile == (int)blockIdx.x) {           // later tiles were prefetched by the previous tile's last step
+                    const float* x0 = xp_row + blk_of(tile, 0) * (2 * kNX) * 128;
+#pragma unroll
+                    for (int j = 0; j < kH; ++j) P[j] = __ldg(x0 + (size_t)j * 128);
+                }
+                tmem_st_wait();
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                mbar_arrive(bar_h);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(bar_h);
-            float head_acc = 0.f;
             for (int s = 0; s < kWindow; ++s, ++g) {
-                const int t = chain ? kWindow - 1 - s : s;
-                const size_t blk = (size_t)tile * kWindow + t;
-                const float* xrow = xp + (blk * (2 * kNX) + chain * kNX) * 128 + row;   // + col * 128
+                const size_t blk = blk_of(tile, s);
+                const float* xb = xp_row + blk * (2 * kNX) * 128;
+                // where the next reset-gate addends come from (next step, or the next tile's first step)
+                const float* xnext = nullptr;
+                if (s + 1 < kWindow) xnext = xp_row + blk_of(tile, s + 1) * (2 * kNX) * 128;
+                else if (tile + (int)gridDim.x < n_tiles) xnext = xp_row + blk_of(tile + gridDim.x, 0) * (2 * kNX) * 128;
                 // ---- G-EPI, reset gate first: the candidate MMA waits for r*h
                 mbar_wait(bar_g, g & 1);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int c0 = 0; c0 < kH; c0 += 16) {
-                    float a[16];
-                    tmem_ld16(t_r + c0, a);
+                    uint32_t ar[16], hr[16];
+                    tmem_ld16_nowait(t_r + c0, ar);
+                    tmem_ld16_nowait(t_h + c0, hr);
+                    tmem_ld_wait();
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float r0 = fast_sigmoid(a[i] + __ldg(xrow + (size_t)(c0 + i) * 128));
-                        const float r1 = fast_sigmoid(a[i + 1] + __ldg(xrow + (size_t)(c0 + i + 1) * 128));
-                        split_bf16x2(r0 * h[c0 + i], r1 * h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
+                    for (int i = 0; i < 16; i += 4) {
+                        float pre[4], r[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            pre[k] = __uint_as_float(ar[i + k]) + P[c0 + i + k];
+                            P[c0 + i + k] = __ldg(xb + (size_t)(kH + c0 + i + k) * 128);     // refill with xp_u
+                        }
+                        sigmoid4(pre, r);
+                        split_bf16x2(r[0] * __uint_as_float(hr[i]), r[1] * __uint_as_float(hr[i + 1]), hi[i >> 1], lo[i >> 1]);
+                        split_bf16x2(r[2] * __uint_as_float(hr[i + 2]), r[3] * __uint_as_float(hr[i + 3]), hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
                     }
                     *reinterpret_cast<uint4*>(a_hi + (c0 / 8) * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(a_hi + (c0 / 8 + 1) * 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -697,35 +726,55 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
                 fence_proxy_async_smem();
                 tc_fence_before_sync();
                 mbar_arrive(bar_rh);
-                // ---- update gate while the candidate MMA runs; stash u in the Dg columns it came from
+                // ---- update gate while the candidate MMA runs; u replaces its own accumulator columns
 #pragma unroll
                 for (int c0 = 0; c0 < kH; c0 += 16) {
                     float a[16];
                     tmem_ld16(t_u + c0, a);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) a[i] = fast_sigmoid(a[i] + __ldg(xrow + (size_t)(kH + c0 + i) * 128));
+                    for (int i = 0; i < 16; i += 4) {
+                        float pre[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            pre[k] = a[i + k] + P[c0 + i + k];
+                            P[c0 + i + k] = __ldg(xb + (size_t)(2 * kH + c0 + i + k) * 128);  // refill with xp_c
+                        }
+                        sigmoid4(pre, a + i);
+                    }
                     tmem_st16(t_u + c0, a);
                 }
                 tmem_st_wait();
                 // ---- C-EPI
                 mbar_wait(bar_c, g & 1);
                 tc_fence_after_sync();
+                float head_acc = 0.f;
 #pragma unroll
                 for (int c0 = 0; c0 < kH; c0 += 16) {
-                    float cc[16], u[16];
-                    tmem_ld16(t_c + c0, cc);
-                    tmem_ld16(t_u + c0, u);
+                    uint32_t cr[16], ur[16], hr[16];
+                    tmem_ld16_nowait(t_c + c0, cr);
+                    tmem_ld16_nowait(t_u + c0, ur);
+                    tmem_ld16_nowait(t_h + c0, hr);
+                    tmem_ld_wait();
                     uint32_t hi[8], lo[8];
+                    float hn[16];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float c_0 = fast_tanh(cc[i] + __ldg(xrow + (size_t)(2 * kH + c0 + i) * 128));
-                        const float c_1 = fast_tanh(cc[i + 1] + __ldg(xrow + (size_t)(2 * kH + c0 + i + 1) * 128));
-                        const float h0 = u[i] * h[c0 + i] + (1.f - u[i]) * c_0;
-                        const float h1 = u[i + 1] * h[c0 + i + 1] + (1.f - u[i + 1]) * c_1;
-                        h[c0 + i] = h0;
-                        h[c0 + i + 1] = h1;
-                        split_bf16x2(h0, h1, hi[i >> 1], lo[i >> 1]);
+                    for (int i = 0; i < 16; i += 4) {
+                        float pre[4], cv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            pre[k] = __uint_as_float(cr[i + k]) + P[c0 + i + k];
+                            if (xnext) P[c0 + i + k] = __ldg(xnext + (size_t)(c0 + i + k) * 128);  // refill with next xp_r
+                        }
+                        tanh4(pre, cv);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float u = __uint_as_float(ur[i + k]);
+                            hn[i + k] = u * __uint_as_float(hr[i + k]) + (1.f - u) * cv[k];
+                        }
                     }
+                    tmem_st16(t_h + c0, hn);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) split_bf16x2(hn[i], hn[i + 1], hi[i >> 1], lo[i >> 1]);
                     *reinterpret_cast<uint4*>(a_hi + (c0 / 8) * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(a_hi + (c0 / 8 + 1) * 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4*>(a_lo + (c0 / 8) * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -738,21 +787,21 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
                         *reinterpret_cast<uint4*>(yb + 128 * 2 * kH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + 128 * 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
-                }
-                if (head_part) {
-                    // dense 128 -> 1: this direction's half of the dot product (rnn_class.py:179)
-                    head_acc = 0.f;
+                    if (head_part) {
+                        // dense 128 -> 1: this direction's half of the dot product (rnn_class.py:179)
 #pragma unroll
-                    for (int j = 0; j < kH; ++j) head_acc = fmaf(h[j], __ldg(head_w + chain * kH + j), head_acc);
-                    head_part[(blk * 2 + chain) * 128 + row] = head_acc;
+                        for (int i = 0; i < 16; ++i) head_acc = fmaf(hn[i], __ldg(head_w + chain * kH + c0 + i), head_acc);
+                    }
                 }
+                if (head_part) head_part[(blk * 2 + chain) * 128 + row] = head_acc;
+                tmem_st_wait();
                 if (s + 1 < kWindow) {
                     fence_proxy_async_smem();
                     tc_fence_before_sync();
                     mbar_arrive(bar_h);
                 }
             }
-            tc_fence_before_sync();      // this tile's TMEM reads precede the next tile's first MMA
+            tc_fence_before_sync();      // this tile's TMEM accesses precede the next tile's first MMA
         }
     }
     tc_fence_before_sync();

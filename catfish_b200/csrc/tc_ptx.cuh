@@ -163,12 +163,14 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 // Pack two floats' hi parts and lo parts into bf16x2 words (element 0 in the low half).
+// Uses the packed conversion (F2FP, FMA/ALU pipes) - the scalar F2F.BF16 runs on the XU pipe,
+// which the GRU epilogue needs for its transcendentals.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(x0, h0, l0);
-    split_bf16(x1, h1, l1);
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ---------------------------------------------------------------- activations (MUFU)
@@ -190,6 +192,38 @@ __device__ __forceinline__ float fast_tanh(float x) {
     // (1 - e) / (1 + e), e = exp(-2|x|): no cancellation for large |x|, ~1e-7 absolute near 0
     const float e = ex2_approx(-2.8853900817779268f * fabsf(x));
     return copysignf((1.f - e) * rcp_approx(1.f + e), x);
+}
+
+// Four reciprocals from one MUFU.RCP: r = 1 / (a0 a1 a2 a3), then back-multiplication.
+// Callers keep every a_i in [1, 5e8] so the product cannot overflow.
+__device__ __forceinline__ void rcp4(const float* a, float* inv) {
+    const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+    const float r = rcp_approx(p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;
+    inv[0] = r01 * a[1];
+    inv[1] = r01 * a[0];
+    inv[2] = r23 * a[3];
+    inv[3] = r23 * a[2];
+}
+// sigmoid of four values: 4 x ex2 + 1 x rcp.  The exponent is clamped at 20 (sigmoid(-20) = 2e-9),
+// which bounds 1 + e^-x by 4.9e8 and the product of four by 5.7e34.
+__device__ __forceinline__ void sigmoid4(const float* x, float* y) {
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 1.f + ex2_approx(fminf(-1.4426950408889634f * x[i], 28.853900817779268f));
+    rcp4(a, y);
+}
+// tanh of four values: (1 - e) / (1 + e), e = exp(-2|x|) in (0, 1]; 4 x ex2 + 1 x rcp.
+__device__ __forceinline__ void tanh4(const float* x, float* y) {
+    float e[4], a[4], inv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        e[i] = ex2_approx(-2.8853900817779268f * fabsf(x[i]));
+        a[i] = 1.f + e[i];
+    }
+    rcp4(a, inv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = copysignf((1.f - e[i]) * inv[i], x[i]);
 }
 
 }  // namespace ptx
