@@ -306,6 +306,14 @@ def run_b200(args):
         roof.update({"kernel": name, "launches": dom_launches, "avg_launch_ms": dom_ms / max(1, dom_launches),
                      "share_of_step": dom_ms / ms_dev, "peak_source": peaks["source"] + " (sustained)",
                      "algorithmic_per_sample": FLOPS_PER_SAMPLE.get(name, BYTES_PER_SAMPLE.get(name))})
+        if prof.get("k3_gru_input_proj", (0.0, 0))[0] == 0.0:
+            # fused GRU layer kernel: projection + recurrence FLOPs both run inside k4
+            FLOPS_PER_SAMPLE["k4_gru_recurrence"] = 221184.0 + 147456.0
+            if name == "k4_gru_recurrence":
+                achieved = FLOPS_PER_SAMPLE[name] * units_per_launch / per_launch_s / 1e12
+                roof.update({"achieved": achieved, "frac": achieved / peaks["tensor_sustained"],
+                             "algorithmic_per_sample": FLOPS_PER_SAMPLE[name],
+                             "note": "fused GRU layer: input projection + recurrence"})
         kernels = {}
         for k, (ms, cnt) in prof.items():
             ent = {"ms": ms, "launches": cnt, "share": ms / ms_dev}

@@ -19,6 +19,7 @@
 // block is one contiguous cp.async.bulk (TMA) copy.  xp is stored per block as [384][128] fp32
 // (column-major), which makes both its producer (TMEM lane = window) and its consumer coalesced.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "model.cuh"
@@ -68,6 +69,7 @@ struct TcLayer {
     float* wx_f32 = nullptr;          // [in][384] fp32                       (in == 1)
     float* bx = nullptr;              // [384]
     __nv_bfloat16* wh = nullptr;      // [dir]{Wg hi, Wg lo [8][128][8]; Wc hi, Wc lo [8][64][8]}
+    uint8_t* wfused = nullptr;        // [dir]{Wgx, Wcx, Wgh, Wch} as in GruFusedCfg (in = 32 or 128)
 };
 
 struct TcEngine {
@@ -81,6 +83,7 @@ struct TcEngine {
     DevBuf ws;
     int n_sms = 148;
     bool attr_done = false;
+    bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
 };
 
 bool tc_supported(const HostModel& hm) {
@@ -105,6 +108,7 @@ TcEngine* tc_create(const HostModel& hm) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, dev);
     e->simt = simt_create(hm);
+    if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
         std::vector<uint8_t> blk(ConvParams::kBytes, 0);
@@ -167,6 +171,17 @@ TcEngine* tc_create(const HostModel& hm) {
             pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wh);
         }
         L.wh = tc_upload(e, wh);
+        if (L.in == kC || L.in == 2 * kH) {
+            std::vector<__nv_bfloat16> wf;
+            for (int d = 0; d < 2; ++d) {
+                const GruDir& g = hm.gru[2 * l + d];
+                pack_b_operand(g.wx.data(), L.in, 2 * kH, kNX, 0, &wf);          // x rows of gates/kernel
+                pack_b_operand(g.wx.data(), L.in, kH, kNX, 2 * kH, &wf);         // x rows of candidate/kernel
+                pack_b_operand(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf);
+                pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wf);
+            }
+            L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, wf));
+        }
         e->layers.push_back(L);
     }
     e->head_w = tc_upload(e, hm.head_w);
@@ -809,9 +824,298 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
     if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
+// ====================================================================== TK4F: fused GRU layer
+// Input projection + recurrence of one GRU layer in one kernel: the concat([x, h]) matmuls of
+// tf.contrib.rnn.GRUCell (rnn_class.py:146) exactly as TensorFlow does them, so the hoisted
+// projection xp never goes to HBM (it was 1536 B/sample/layer written and read back).
+//
+// CTA = one direction, one tile of 128 windows at a time (persistent over tiles).  Resident in
+// shared memory: the direction's weights [x rows; h rows] x [r|u|c] as split-bf16 B operands
+// (147 KB for a 128-wide input), the state operand h / r*h (32 KB) and a 4-stage ring through
+// which the layer input x_t streams in K = 16 chunks by bulk TMA copies.  Two TMEM accumulator
+// sets (gates 128 + candidate 64 columns each): while the epilogue works on step s, the tensor
+// core already accumulates the x part of step s+1 into the other set - only the K = 64 state
+// part of each matmul sits on the recurrent critical path.
+//   warps 0-7 : epilogue; thread = (window, half of the hidden units), h and u in registers
+//   warp 8    : MMA issuer (+ TMEM owner); candidate-state MMAs take priority over x chunks
+//   warp 9    : producer (weights once, then the x ring)
+template <int KX> struct GruFusedCfg {
+    static constexpr int kChunks = KX / 16;                              // x K-chunks per step
+    static constexpr int kStages = 4;
+    static constexpr uint32_t kWgx = 0;                                  // {hi, lo} x [KX/8][128][8]
+    static constexpr uint32_t kWcx = kWgx + 2u * KX * 128 * 2;           // {hi, lo} x [KX/8][64][8]
+    static constexpr uint32_t kWgh = kWcx + 2u * KX * 64 * 2;            // {hi, lo} x [8][128][8]
+    static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;           // {hi, lo} x [8][64][8]
+    static constexpr uint32_t kWBytes = kWch + 2u * kH * 64 * 2;         // (KX + 64) * 192 * 4
+    static constexpr uint32_t kHBuf = kWBytes;                           // {hi, lo} x [8][128][8]
+    static constexpr uint32_t kRing = kHBuf + kGruABytes;                // kStages x {hi, lo} x [2][128][8]
+    static constexpr uint32_t kBias = kRing + kStages * 8192;            // 192 floats
+    static constexpr uint32_t kBars = kBias + 192 * 4;
+    static constexpr uint32_t kSmem = kBars + 256;
+};
+
+template <int KX>
+__global__ void __launch_bounds__(320, 1)
+tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
+                    const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
+                    const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles) {
+    using Cfg = GruFusedCfg<KX>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
+    uint64_t* bar_g = &bars[0];
+    uint64_t* bar_c = &bars[1];
+    uint64_t* bar_rh = &bars[2];
+    uint64_t* bar_h = &bars[3];
+    uint64_t* full = &bars[4];                    // [kStages]
+    uint64_t* empty = &bars[4 + Cfg::kStages];    // [kStages]
+    uint64_t* w_bar = &bars[4 + 2 * Cfg::kStages];
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[5 + 2 * Cfg::kStages]);
+    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x & 1;
+    const int slot = blockIdx.x >> 1, n_slots = gridDim.x >> 1;
+    const int my_tiles = slot < n_tiles ? (n_tiles - slot + n_slots - 1) / n_slots : 0;
+    const int total_steps = my_tiles * kWindow;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_g, 1);
+        mbar_init(bar_c, 1);
+        mbar_init(bar_rh, 256);
+        mbar_init(bar_h, 256);
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+    }
+    if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x];
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    // block (tile, t) visited at flattened step gs of this CTA
+    auto blk_of = [&](int gs) -> size_t {
+        const int ti = gs / kWindow, s = gs - ti * kWindow;
+        return (size_t)(slot + ti * n_slots) * kWindow + (dir ? kWindow - 1 - s : s);
+    };
+
+    if (warp == 9) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, Cfg::kWBytes);
+            const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
+            for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
+                const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
+                bulk_g2s(smem + off, wsrc + off, n, w_bar);
+            }
+            constexpr size_t plane = (size_t)128 * KX * 2;          // bytes of one plane of an x block
+            uint32_t c = 0;
+            for (int gs = 0; gs < total_steps; ++gs) {
+                const uint8_t* xb = reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs) * 2 * plane;
+                for (int kk = 0; kk < Cfg::kChunks; ++kk, ++c) {
+                    const int st = c % Cfg::kStages;
+                    mbar_wait(&empty[st], ((c / Cfg::kStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[st], 8192);
+                    uint8_t* dst = smem + Cfg::kRing + st * 8192;
+                    bulk_g2s(dst, xb + kk * 4096, 4096, &full[st]);
+                    bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, &full[st]);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
+            constexpr uint32_t idesc_c = make_idesc_bf16(128, kH);
+            const uint32_t s0 = smem_u32(smem);
+            const uint32_t hbuf = s0 + Cfg::kHBuf, ring = s0 + Cfg::kRing;
+            uint32_t c = 0;                          // x chunks consumed so far
+            // x part of one chunk of step `gs_next` into accumulator set `buf`
+            auto issue_x_chunk = [&](int kk, uint32_t buf) {
+                const int st = c % Cfg::kStages;
+                const uint32_t a0 = ring + st * 8192;
+                const uint32_t dg = tmem + buf * 256, dc = dg + 2 * kH;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
+                    const uint32_t wg = s0 + Cfg::kWgx + (pass == 2 ? (uint32_t)KX * 128 * 2 : 0u) + kk * 2 * (128 * 16);
+                    const uint32_t wc = s0 + Cfg::kWcx + (pass == 2 ? (uint32_t)KX * 64 * 2 : 0u) + kk * 2 * (64 * 16);
+                    umma_bf16(dg, ad, make_smem_desc(wg, 128 * 16, 128), idesc_g, (kk | pass) != 0);
+                    umma_bf16(dc, ad, make_smem_desc(wc, 64 * 16, 128), idesc_c, (kk | pass) != 0);
+                }
+                umma_commit(&empty[st]);
+                ++c;
+            };
+            mbar_wait(w_bar, 0);
+            if (total_steps > 0) {
+                for (int kk = 0; kk < Cfg::kChunks; ++kk) {            // prologue: x part of step 0
+                    mbar_wait(&full[c % Cfg::kStages], (c / Cfg::kStages) & 1);
+                    tc_fence_after_sync();
+                    issue_x_chunk(kk, 0);
+                }
+            }
+            for (int gs = 0; gs < total_steps; ++gs) {
+                const uint32_t buf = gs & 1, par = gs & 1;
+                const uint32_t dg = tmem + buf * 256, dc = dg + 2 * kH;
+                mbar_wait(bar_h, par);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {                 // state part of the gates
+                    const uint32_t ap = hbuf + (pass == 1 ? 128u * kH * 2 : 0u);
+                    const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
+#pragma unroll
+                    for (int kk = 0; kk < kH / 16; ++kk)
+                        umma_bf16(dg, make_smem_desc(ap + kk * 4096, 2048, 128),
+                                  make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1);
+                }
+                umma_commit(bar_g);
+                int xk = 0;
+                const int nx = gs + 1 < total_steps ? Cfg::kChunks : 0;
+                bool c_done = false;
+                while (xk < nx || !c_done) {
+                    if (!c_done && mbar_try_wait(bar_rh, par)) {
+                        tc_fence_after_sync();
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {         // state part of the candidate
+                            const uint32_t ap = hbuf + (pass == 1 ? 128u * kH * 2 : 0u);
+                            const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
+#pragma unroll
+                            for (int kk = 0; kk < kH / 16; ++kk)
+                                umma_bf16(dc, make_smem_desc(ap + kk * 4096, 2048, 128),
+                                          make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1);
+                        }
+                        umma_commit(bar_c);
+                        c_done = true;
+                    } else if (xk < nx && mbar_try_wait(&full[c % Cfg::kStages], (c / Cfg::kStages) & 1)) {
+                        tc_fence_after_sync();
+                        issue_x_chunk(xk, buf ^ 1);
+                        ++xk;
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int q = warp & 3, hf = warp >> 2;          // TMEM lane quadrant, half of the hidden units
+        const int row = q * 32 + lane;
+        const int j0 = hf * 32;
+        uint8_t* a_hi = smem + Cfg::kHBuf + row * 16;    // + (k/8) * 2048
+        uint8_t* a_lo = a_hi + 128 * kH * 2;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        float h[32], u[32];
+        int gs = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = 0.f;
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                *reinterpret_cast<uint4*>(a_hi + (hf * 4 + kg) * 2048) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(a_lo + (hf * 4 + kg) * 2048) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            mbar_arrive(bar_h);
+            for (int s = 0; s < kWindow; ++s, ++gs) {
+                const uint32_t par = gs & 1;
+                const uint32_t tb = t_lane + (gs & 1) * 256 + j0;
+                const size_t blk = blk_of(gs);
+                // ---- reset gate, r*h to the operand buffer
+                mbar_wait(bar_g, par);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    float a[16];
+                    tmem_ld16(tb + c0, a);
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float pre[4], r[4];
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + c0 + i);
+                        pre[0] = a[i] + b4.x; pre[1] = a[i + 1] + b4.y; pre[2] = a[i + 2] + b4.z; pre[3] = a[i + 3] + b4.w;
+                        sigmoid4(pre, r);
+                        split_bf16x2(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
+                        split_bf16x2(r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                    }
+                    const int kg = (j0 + c0) / 8;
+                    *reinterpret_cast<uint4*>(a_hi + kg * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(a_hi + (kg + 1) * 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(a_lo + kg * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_lo + (kg + 1) * 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                mbar_arrive(bar_rh);
+                // ---- update gate while the candidate MMA runs
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    float a[16];
+                    tmem_ld16(tb + kH + c0, a);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float pre[4];
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + kH + j0 + c0 + i);
+                        pre[0] = a[i] + b4.x; pre[1] = a[i + 1] + b4.y; pre[2] = a[i + 2] + b4.z; pre[3] = a[i + 3] + b4.w;
+                        sigmoid4(pre, u + c0 + i);
+                    }
+                }
+                // ---- candidate, new state
+                mbar_wait(bar_c, par);
+                tc_fence_after_sync();
+                float head_acc = 0.f;
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    float a[16];
+                    tmem_ld16(tb + 2 * kH + c0, a);
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float pre[4], cv[4];
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * kH + j0 + c0 + i);
+                        pre[0] = a[i] + b4.x; pre[1] = a[i + 1] + b4.y; pre[2] = a[i + 2] + b4.z; pre[3] = a[i + 3] + b4.w;
+                        tanh4(pre, cv);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = c0 + i + k;
+                            h[j] = u[j] * h[j] + (1.f - u[j]) * cv[k];
+                        }
+                        split_bf16x2(h[c0 + i], h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
+                        split_bf16x2(h[c0 + i + 2], h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                    }
+                    const int kg = (j0 + c0) / 8;
+                    *reinterpret_cast<uint4*>(a_hi + kg * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(a_hi + (kg + 1) * 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(a_lo + kg * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_lo + (kg + 1) * 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (y_out) {
+                        // next layer's A operand: block {hi, lo} x [16][128][8], features dir*64 + j
+                        __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0 + c0) / 8 * 128 + row) * 8;
+                        *reinterpret_cast<uint4*>(yb) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(yb + 128 * 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        *reinterpret_cast<uint4*>(yb + 128 * 2 * kH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + 128 * 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                    if (head_part) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) head_acc = fmaf(h[c0 + i], __ldg(head_w + dir * kH + j0 + c0 + i), head_acc);
+                    }
+                }
+                if (head_part) head_part[((blk * 2 + dir) * 2 + hf) * 128 + row] = head_acc;
+                tc_fence_before_sync();
+                if (s + 1 < kWindow) {
+                    fence_proxy_async_smem();
+                    mbar_arrive(bar_h);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
 // ====================================================================== TK5: head
 // p = sigmoid(part_fw + part_bw + b), scattered to sample order with the padding cut (infer.py:47).
-__global__ void tc_head_kernel(const float* __restrict__ head_part, float b, const int64_t* __restrict__ src,
+__global__ void tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const int64_t* __restrict__ src,
                                const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
                                const double* __restrict__ stats, int64_t tile0, int64_t n_rows,
                                float* __restrict__ probs) {
@@ -824,7 +1128,8 @@ __global__ void tc_head_kernel(const float* __restrict__ head_part, float b, con
     const int64_t g = (tile0 + tile) * kTileWindows + w;
     if (t >= valid[g]) return;
     const size_t blk = (size_t)tile * kWindow + t;
-    const float acc = head_part[(blk * 2) * 128 + w] + head_part[(blk * 2 + 1) * 128 + w] + b;
+    float acc = b;
+    for (int k = 0; k < n_parts; ++k) acc += head_part[(blk * n_parts + k) * 128 + w];
     float p = 1.f / (1.f + expf(-acc));
     if (stats) {
         const double sc = stats[2 * read[g] + 1];
@@ -844,7 +1149,7 @@ static size_t tc_workspace_bytes(const HostModel& hm, int64_t tiles) {
     b += blocks * 128 * kC * 2 * 2;          // conv output as A operand (K = 32)
     b += blocks * 2 * kNX * 128 * 4;         // xp
     b += 2 * blocks * 128 * 2 * kH * 2 * 2;  // y ping-pong (K = 128 operands)
-    b += blocks * 2 * 128 * 4;               // head partials
+    b += blocks * 4 * 128 * 4;               // head partials
     return b + 4096;
 }
 
@@ -855,6 +1160,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<32>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
@@ -895,8 +1202,34 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         } else {
             CF_TRY(simt_conv_stack(e->simt, hm, raw, stats, xwin, tab, tile0, tiles, chunk, &feat, stream, prof));
         }
+        int head_parts = 2;
         for (int l = 0; l < n_layers; ++l) {
             const TcLayer& L = e->layers[l];
+            const bool last = l + 1 == n_layers;
+            __nv_bfloat16* yo = last ? nullptr : ybuf[l & 1];
+            if (L.wfused && e->use_fused) {
+                // input projection + recurrence in one kernel; a_in is the A-operand form of the layer input
+                if (l == 0 && !a_in) {
+                    ProfScope ps(prof, KC_K3_XPROJ, stream);
+                    const int64_t total = rows * (kC / 8);
+                    tc_pack_a_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(feat, kC, rows, a0);
+                    CF_LAUNCHED();
+                    a_in = a0;
+                }
+                ProfScope ps(prof, KC_K4_GRU, stream);
+                const int grid = 2 * (int)std::min<int64_t>(tiles, e->n_sms / 2);
+                if (L.in == kC)
+                    tc_gru_fused_kernel<32><<<grid, 320, GruFusedCfg<32>::kSmem, stream>>>(
+                        L.wfused, L.bx, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                else
+                    tc_gru_fused_kernel<128><<<grid, 320, GruFusedCfg<128>::kSmem, stream>>>(
+                        L.wfused, L.bx, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                CF_LAUNCHED();
+                a_in = yo;
+                head_parts = 4;
+                continue;
+            }
+            head_parts = 2;
             {
                 ProfScope ps(prof, KC_K3_XPROJ, stream);
                 if (L.in == 1) {
@@ -921,8 +1254,6 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             }
             {
                 ProfScope ps(prof, KC_K4_GRU, stream);
-                const bool last = l + 1 == n_layers;
-                __nv_bfloat16* yo = last ? nullptr : ybuf[l & 1];
                 const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
                 tc_gru_kernel<<<grid, 320, kGruSmem, stream>>>(L.wh, xp, yo, last ? e->head_w : nullptr,
                                                                last ? head_part : nullptr, (int)tiles);
@@ -933,7 +1264,7 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         {
             ProfScope ps(prof, KC_K5_HEAD, stream);
             tc_head_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
-                head_part, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);
+                head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);
             CF_LAUNCHED();
         }
     }
