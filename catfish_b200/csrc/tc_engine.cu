@@ -33,6 +33,8 @@ constexpr int kH = 64;            // GRU units
 constexpr int kC = 32;            // conv channels
 constexpr int kNX = 3 * kH;       // 192 projection columns per direction (r | u | c)
 constexpr int kTcChunkTiles = 592;   // tiles per internal pass (4 waves of 148 CTAs)
+constexpr float kGateScale = -1.4426950408889634f;    // -log2(e)
+constexpr float kCandScale = 2.8853900817779268f;     // 2 log2(e)
 
 struct ConvParams {                    // byte offsets inside the parameter block
     static constexpr int kFloats = 10 * 32;              // a_sc b_sc a1 b1 | b2 b3 b4 b5 b6 b7
@@ -46,7 +48,8 @@ struct ConvParams {                    // byte offsets inside the parameter bloc
 
 // ====================================================================== weight packing (host)
 // B operand of D = A * W for W [K][N] row-major: stored [plane][K/8][N][8] with plane 0 = hi.
-static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std::vector<__nv_bfloat16>* out) {
+static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std::vector<__nv_bfloat16>* out,
+                           float scale = 1.f) {
     const size_t plane = (size_t)K * N;
     const size_t base = out->size();
     out->resize(base + 2 * plane);
@@ -54,7 +57,7 @@ static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std:
     __nv_bfloat16* lo = hi + plane;
     for (int k = 0; k < K; ++k)
         for (int n = 0; n < N; ++n) {
-            const float v = w[(size_t)k * ldw + col0 + n];
+            const float v = w[(size_t)k * ldw + col0 + n] * scale;
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
             const size_t idx = ((size_t)(k / 8) * N + n) * 8 + (k % 8);
@@ -69,7 +72,8 @@ struct TcLayer {
     float* wx_f32 = nullptr;          // [in][384] fp32                       (in == 1)
     float* bx = nullptr;              // [384]
     __nv_bfloat16* wh = nullptr;      // [dir]{Wg hi, Wg lo [8][128][8]; Wc hi, Wc lo [8][64][8]}
-    uint8_t* wfused = nullptr;        // [dir]{Wgx, Wcx, Wgh, Wch} as in GruFusedCfg (in = 32 or 128)
+    uint8_t* wfused = nullptr;        // [dir]{Wgx, Wcx, Wgh, Wch} as in GruFusedCfg (in = 32 or 128), exponent domain
+    float* bz = nullptr;              // [384] biases in the exponent domain
 };
 
 struct TcEngine {
@@ -83,6 +87,7 @@ struct TcEngine {
     DevBuf ws;
     int n_sms = 148;
     bool attr_done = false;
+    int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
 };
 
@@ -109,6 +114,7 @@ TcEngine* tc_create(const HostModel& hm) {
     cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, dev);
     e->simt = simt_create(hm);
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
+    if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
         std::vector<uint8_t> blk(ConvParams::kBytes, 0);
@@ -175,12 +181,18 @@ TcEngine* tc_create(const HostModel& hm) {
             std::vector<__nv_bfloat16> wf;
             for (int d = 0; d < 2; ++d) {
                 const GruDir& g = hm.gru[2 * l + d];
-                pack_b_operand(g.wx.data(), L.in, 2 * kH, kNX, 0, &wf);          // x rows of gates/kernel
-                pack_b_operand(g.wx.data(), L.in, kH, kNX, 2 * kH, &wf);         // x rows of candidate/kernel
-                pack_b_operand(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf);
-                pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wf);
+                // exponent domain: gates scaled by -log2(e), candidate by 2 log2(e) (see sigmoid4_z / tanh4_z)
+                pack_b_operand(g.wx.data(), L.in, 2 * kH, kNX, 0, &wf, kGateScale);       // x rows of gates/kernel
+                pack_b_operand(g.wx.data(), L.in, kH, kNX, 2 * kH, &wf, kCandScale);      // x rows of candidate/kernel
+                pack_b_operand(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale);
+                pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale);
             }
             L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, wf));
+            std::vector<float> bz(2 * kNX);
+            for (int d = 0; d < 2; ++d)
+                for (int j = 0; j < kNX; ++j)
+                    bz[d * kNX + j] = hm.gru[2 * l + d].bx[j] * (j < 2 * kH ? kGateScale : kCandScale);
+            L.bz = tc_upload(e, bz);
         }
         e->layers.push_back(L);
     }
@@ -836,12 +848,12 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
 // sets (gates 128 + candidate 64 columns each): while the epilogue works on step s, the tensor
 // core already accumulates the x part of step s+1 into the other set - only the K = 64 state
 // part of each matmul sits on the recurrent critical path.
-//   warps 0-7 : epilogue; thread = (window, half of the hidden units), h and u in registers
-//   warp 8    : MMA issuer (+ TMEM owner); candidate-state MMAs take priority over x chunks
-//   warp 9    : producer (weights once, then the x ring)
+//   warps 0-15: epilogue; thread = (window, quarter of the hidden units), h and u in registers
+//   warp 16   : MMA issuer (+ TMEM owner); candidate-state MMAs take priority over x chunks
+//   warp 17   : producer (weights once, then the x ring)
 template <int KX> struct GruFusedCfg {
     static constexpr int kChunks = KX / 16;                              // x K-chunks per step
-    static constexpr int kStages = 4;
+    static constexpr int kStages = KX >= 128 ? 5 : 8;
     static constexpr uint32_t kWgx = 0;                                  // {hi, lo} x [KX/8][128][8]
     static constexpr uint32_t kWcx = kWgx + 2u * KX * 128 * 2;           // {hi, lo} x [KX/8][64][8]
     static constexpr uint32_t kWgh = kWcx + 2u * KX * 64 * 2;            // {hi, lo} x [8][128][8]
@@ -855,10 +867,10 @@ template <int KX> struct GruFusedCfg {
 };
 
 template <int KX>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                     const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
-                    const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles) {
+                    const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int dbg) {
     using Cfg = GruFusedCfg<KX>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
@@ -881,14 +893,14 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
     if (threadIdx.x == 0) {
         mbar_init(bar_g, 1);
         mbar_init(bar_c, 1);
-        mbar_init(bar_rh, 256);
-        mbar_init(bar_h, 256);
+        mbar_init(bar_rh, 512);
+        mbar_init(bar_h, 512);
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(w_bar, 1);
         fence_mbar_init();
     }
     if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x];
-    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (warp == 16) tmem_alloc<512>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -899,7 +911,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
         return (size_t)(slot + ti * n_slots) * kWindow + (dir ? kWindow - 1 - s : s);
     };
 
-    if (warp == 9) {
+    if (warp == 17) {
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             mbar_expect_tx(w_bar, Cfg::kWBytes);
@@ -910,11 +922,17 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
             }
             constexpr size_t plane = (size_t)128 * KX * 2;          // bytes of one plane of an x block
             uint32_t c = 0;
+            constexpr int kAhead = 3;                 // blocks pulled into L2 ahead of the ring (hides HBM latency)
+            for (int gs = 0; gs < kAhead && gs < total_steps; ++gs)
+                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs) * 2 * plane, 2 * plane);
             for (int gs = 0; gs < total_steps; ++gs) {
                 const uint8_t* xb = reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs) * 2 * plane;
+                if (gs + kAhead < total_steps)
+                    bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs + kAhead) * 2 * plane, 2 * plane);
                 for (int kk = 0; kk < Cfg::kChunks; ++kk, ++c) {
                     const int st = c % Cfg::kStages;
                     mbar_wait(&empty[st], ((c / Cfg::kStages) & 1) ^ 1);
+                    if (dbg & 1) { mbar_arrive(&full[st]); continue; }      // timing experiment: no x traffic
                     mbar_expect_tx(&full[st], 8192);
                     uint8_t* dst = smem + Cfg::kRing + st * 8192;
                     bulk_g2s(dst, xb + kk * 4096, 4096, &full[st]);
@@ -922,7 +940,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
@@ -936,7 +954,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
                 const uint32_t a0 = ring + st * 8192;
                 const uint32_t dg = tmem + buf * 256, dc = dg + 2 * kH;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
+                for (int pass = 0; pass < ((dbg & 2) ? 1 : 3); ++pass) {   // dbg & 2: timing experiment, single pass
                     const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
                     const uint32_t wg = s0 + Cfg::kWgx + (pass == 2 ? (uint32_t)KX * 128 * 2 : 0u) + kk * 2 * (128 * 16);
                     const uint32_t wc = s0 + Cfg::kWcx + (pass == 2 ? (uint32_t)KX * 64 * 2 : 0u) + kk * 2 * (64 * 16);
@@ -973,7 +991,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
                 const int nx = gs + 1 < total_steps ? Cfg::kChunks : 0;
                 bool c_done = false;
                 while (xk < nx || !c_done) {
-                    if (!c_done && mbar_try_wait(bar_rh, par)) {
+                    if (!c_done && mbar_test_wait(bar_rh, par)) {
                         tc_fence_after_sync();
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {         // state part of the candidate
@@ -986,7 +1004,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
                         }
                         umma_commit(bar_c);
                         c_done = true;
-                    } else if (xk < nx && mbar_try_wait(&full[c % Cfg::kStages], (c / Cfg::kStages) & 1)) {
+                    } else if (xk < nx && mbar_test_wait(&full[c % Cfg::kStages], (c / Cfg::kStages) & 1)) {
                         tc_fence_after_sync();
                         issue_x_chunk(xk, buf ^ 1);
                         ++xk;
@@ -996,121 +1014,119 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
         }
     } else {
         // ------------------------------------------------------------ epilogue
-        const int q = warp & 3, hf = warp >> 2;          // TMEM lane quadrant, half of the hidden units
+        // 16 warps: TMEM lane quadrant q = warp % 4 (hardware rule), quarter qt of the hidden units.
+        const int q = warp & 3, qt = warp >> 2;
         const int row = q * 32 + lane;
-        const int j0 = hf * 32;
-        uint8_t* a_hi = smem + Cfg::kHBuf + row * 16;    // + (k/8) * 2048
+        const int j0 = qt * 16;
+        uint8_t* a_hi = smem + Cfg::kHBuf + row * 16 + (j0 / 8) * 2048;      // two k-groups: +0, +2048
         uint8_t* a_lo = a_hi + 128 * kH * 2;
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-        float h[32], u[32];
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + j0;
+        const float4* b_r = reinterpret_cast<const float4*>(bias_s + j0);
+        const float4* b_u = reinterpret_cast<const float4*>(bias_s + kH + j0);
+        const float4* b_c = reinterpret_cast<const float4*>(bias_s + 2 * kH + j0);
+        const float* hw = head_w ? head_w + dir * kH + j0 : nullptr;
+        float h[16], u[16];
         int gs = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = 0.f;
-#pragma unroll
-            for (int kg = 0; kg < 4; ++kg) {
-                *reinterpret_cast<uint4*>(a_hi + (hf * 4 + kg) * 2048) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(a_lo + (hf * 4 + kg) * 2048) = make_uint4(0, 0, 0, 0);
-            }
+            for (int j = 0; j < 16; ++j) h[j] = 0.f;
+            *reinterpret_cast<uint4*>(a_hi) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(a_hi + 2048) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(a_lo) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(a_lo + 2048) = make_uint4(0, 0, 0, 0);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             mbar_arrive(bar_h);
             for (int s = 0; s < kWindow; ++s, ++gs) {
                 const uint32_t par = gs & 1;
-                const uint32_t tb = t_lane + (gs & 1) * 256 + j0;
+                const uint32_t tb = t_lane + (gs & 1) * 256;
                 const size_t blk = blk_of(gs);
-                // ---- reset gate, r*h to the operand buffer
+                // ---- gates: both TMEM loads in flight, reset gate first (the candidate MMA waits for r*h)
                 mbar_wait(bar_g, par);
                 tc_fence_after_sync();
-#pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    float a[16];
-                    tmem_ld16(tb + c0, a);
+                uint32_t ar[16], au[16];
+                tmem_ld16_nowait(tb, ar);
+                tmem_ld16_nowait(tb + kH, au);
+                tmem_ld_wait();
+                {
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        float pre[4], r[4];
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + c0 + i);
-                        pre[0] = a[i] + b4.x; pre[1] = a[i + 1] + b4.y; pre[2] = a[i + 2] + b4.z; pre[3] = a[i + 3] + b4.w;
-                        sigmoid4(pre, r);
-                        split_bf16x2(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
-                        split_bf16x2(r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                        float z[4], r[4];
+                        const float4 b4 = b_r[i >> 2];
+                        z[0] = __uint_as_float(ar[i]) + b4.x; z[1] = __uint_as_float(ar[i + 1]) + b4.y;
+                        z[2] = __uint_as_float(ar[i + 2]) + b4.z; z[3] = __uint_as_float(ar[i + 3]) + b4.w;
+                        sigmoid4_z(z, r);
+                        split_bf16x2(r[0] * h[i], r[1] * h[i + 1], hi[i >> 1], lo[i >> 1]);
+                        split_bf16x2(r[2] * h[i + 2], r[3] * h[i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
                     }
-                    const int kg = (j0 + c0) / 8;
-                    *reinterpret_cast<uint4*>(a_hi + kg * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(a_hi + (kg + 1) * 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(a_lo + kg * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(a_lo + (kg + 1) * 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(a_hi + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_lo + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
                 fence_proxy_async_smem();
                 tc_fence_before_sync();
                 mbar_arrive(bar_rh);
                 // ---- update gate while the candidate MMA runs
 #pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    float a[16];
-                    tmem_ld16(tb + kH + c0, a);
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float pre[4];
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + kH + j0 + c0 + i);
-                        pre[0] = a[i] + b4.x; pre[1] = a[i + 1] + b4.y; pre[2] = a[i + 2] + b4.z; pre[3] = a[i + 3] + b4.w;
-                        sigmoid4(pre, u + c0 + i);
-                    }
+                for (int i = 0; i < 16; i += 4) {
+                    float z[4];
+                    const float4 b4 = b_u[i >> 2];
+                    z[0] = __uint_as_float(au[i]) + b4.x; z[1] = __uint_as_float(au[i + 1]) + b4.y;
+                    z[2] = __uint_as_float(au[i + 2]) + b4.z; z[3] = __uint_as_float(au[i + 3]) + b4.w;
+                    sigmoid4_z(z, u + i);
                 }
-                // ---- candidate, new state
+                // ---- candidate, new state h = c + u (h - c)
                 mbar_wait(bar_c, par);
                 tc_fence_after_sync();
-                float head_acc = 0.f;
-#pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    float a[16];
-                    tmem_ld16(tb + 2 * kH + c0, a);
+                uint32_t ac[16];
+                tmem_ld16_nowait(tb + 2 * kH, ac);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                {
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        float pre[4], cv[4];
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * kH + j0 + c0 + i);
-                        pre[0] = a[i] + b4.x; pre[1] = a[i + 1] + b4.y; pre[2] = a[i + 2] + b4.z; pre[3] = a[i + 3] + b4.w;
-                        tanh4(pre, cv);
+                        float z[4], cv[4];
+                        const float4 b4 = b_c[i >> 2];
+                        z[0] = __uint_as_float(ac[i]) + b4.x; z[1] = __uint_as_float(ac[i + 1]) + b4.y;
+                        z[2] = __uint_as_float(ac[i + 2]) + b4.z; z[3] = __uint_as_float(ac[i + 3]) + b4.w;
+                        tanh4_z(z, cv);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int j = c0 + i + k;
-                            h[j] = u[j] * h[j] + (1.f - u[j]) * cv[k];
-                        }
-                        split_bf16x2(h[c0 + i], h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
-                        split_bf16x2(h[c0 + i + 2], h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                        for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
+                        split_bf16x2(h[i], h[i + 1], hi[i >> 1], lo[i >> 1]);
+                        split_bf16x2(h[i + 2], h[i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
                     }
-                    const int kg = (j0 + c0) / 8;
-                    *reinterpret_cast<uint4*>(a_hi + kg * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(a_hi + (kg + 1) * 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(a_lo + kg * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(a_lo + (kg + 1) * 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(a_hi + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_lo + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (s + 1 < kWindow) {               // hand h to the next step before the global stores
+                        fence_proxy_async_smem();
+                        mbar_arrive(bar_h);
+                    }
                     if (y_out) {
                         // next layer's A operand: block {hi, lo} x [16][128][8], features dir*64 + j
-                        __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0 + c0) / 8 * 128 + row) * 8;
+                        __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 8;
                         *reinterpret_cast<uint4*>(yb) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4*>(yb + 128 * 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                         *reinterpret_cast<uint4*>(yb + 128 * 2 * kH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + 128 * 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
-                    if (head_part) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) head_acc = fmaf(h[c0 + i], __ldg(head_w + dir * kH + j0 + c0 + i), head_acc);
-                    }
                 }
-                if (head_part) head_part[((blk * 2 + dir) * 2 + hf) * 128 + row] = head_acc;
-                tc_fence_before_sync();
-                if (s + 1 < kWindow) {
-                    fence_proxy_async_smem();
-                    mbar_arrive(bar_h);
+                if (head_part) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc = fmaf(h[i], __ldg(hw + i), acc);
+                    head_part[((blk * 2 + dir) * 4 + qt) * 128 + row] = acc;
                 }
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem);
+    if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
 // ====================================================================== TK5: head
@@ -1149,7 +1165,7 @@ static size_t tc_workspace_bytes(const HostModel& hm, int64_t tiles) {
     b += blocks * 128 * kC * 2 * 2;          // conv output as A operand (K = 32)
     b += blocks * 2 * kNX * 128 * 4;         // xp
     b += 2 * blocks * 128 * 2 * kH * 2 * 2;  // y ping-pong (K = 128 operands)
-    b += blocks * 4 * 128 * 4;               // head partials
+    b += blocks * 8 * 128 * 4;               // head partials
     return b + 4096;
 }
 
@@ -1219,14 +1235,14 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 ProfScope ps(prof, KC_K4_GRU, stream);
                 const int grid = 2 * (int)std::min<int64_t>(tiles, e->n_sms / 2);
                 if (L.in == kC)
-                    tc_gru_fused_kernel<32><<<grid, 320, GruFusedCfg<32>::kSmem, stream>>>(
-                        L.wfused, L.bx, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                    tc_gru_fused_kernel<32><<<grid, 576, GruFusedCfg<32>::kSmem, stream>>>(
+                        L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->dbg);
                 else
-                    tc_gru_fused_kernel<128><<<grid, 320, GruFusedCfg<128>::kSmem, stream>>>(
-                        L.wfused, L.bx, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                    tc_gru_fused_kernel<128><<<grid, 576, GruFusedCfg<128>::kSmem, stream>>>(
+                        L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->dbg);
                 CF_LAUNCHED();
                 a_in = yo;
-                head_parts = 4;
+                head_parts = 8;
                 continue;
             }
             head_parts = 2;

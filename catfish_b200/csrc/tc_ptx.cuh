@@ -46,6 +46,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time): use this
+// when polling several barriers in turn.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -70,6 +83,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// L2 prefetch of a contiguous global range (no shared-memory destination, no completion event)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 
 // ---------------------------------------------------------------- TMEM
@@ -224,6 +242,25 @@ __device__ __forceinline__ void tanh4(const float* x, float* y) {
     rcp4(a, inv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) y[i] = copysignf((1.f - e[i]) * inv[i], x[i]);
+}
+
+// Exponent-domain variants for pre-activations that were already multiplied by -log2(e)
+// (sigmoid) or by 2 log2(e) (tanh) when the weights were packed: one instruction less per value.
+//   sigmoid(x) = 1 / (1 + 2^z),      z = -x log2 e
+//   tanh(x)    = 1 - 2 / (1 + 2^z),  z = 2 x log2 e     (absolute error ~1e-7 near 0)
+__device__ __forceinline__ void sigmoid4_z(const float* z, float* y) {
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 1.f + ex2_approx(fminf(z[i], 28.853900817779268f));
+    rcp4(a, y);
+}
+__device__ __forceinline__ void tanh4_z(const float* z, float* y) {
+    float a[4], inv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 1.f + ex2_approx(fminf(z[i], 28.853900817779268f));
+    rcp4(a, inv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fmaf(-2.f, inv[i], 1.f);
 }
 
 }  // namespace ptx
