@@ -49,7 +49,7 @@ struct ConvParams {                    // byte offsets inside the parameter bloc
 // ====================================================================== weight packing (host)
 // B operand of D = A * W for W [K][N] row-major: stored [plane][K/8][N][8] with plane 0 = hi.
 static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std::vector<__nv_bfloat16>* out,
-                           float scale = 1.f) {
+                           float scale = 1.f, int n_split = 1 << 30, float scale_hi = 1.f) {
     const size_t plane = (size_t)K * N;
     const size_t base = out->size();
     out->resize(base + 2 * plane);
@@ -57,7 +57,7 @@ static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std:
     __nv_bfloat16* lo = hi + plane;
     for (int k = 0; k < K; ++k)
         for (int n = 0; n < N; ++n) {
-            const float v = w[(size_t)k * ldw + col0 + n] * scale;
+            const float v = w[(size_t)k * ldw + col0 + n] * (n < n_split ? scale : scale_hi);
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
             const size_t idx = ((size_t)(k / 8) * N + n) * 8 + (k % 8);
@@ -87,6 +87,7 @@ struct TcEngine {
     DevBuf ws;
     int n_sms = 148;
     bool attr_done = false;
+    int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
 };
@@ -115,6 +116,7 @@ TcEngine* tc_create(const HostModel& hm) {
     e->simt = simt_create(hm);
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
     if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
+    if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
         std::vector<uint8_t> blk(ConvParams::kBytes, 0);
@@ -182,8 +184,8 @@ TcEngine* tc_create(const HostModel& hm) {
             for (int d = 0; d < 2; ++d) {
                 const GruDir& g = hm.gru[2 * l + d];
                 // exponent domain: gates scaled by -log2(e), candidate by 2 log2(e) (see sigmoid4_z / tanh4_z)
-                pack_b_operand(g.wx.data(), L.in, 2 * kH, kNX, 0, &wf, kGateScale);       // x rows of gates/kernel
-                pack_b_operand(g.wx.data(), L.in, kH, kNX, 2 * kH, &wf, kCandScale);      // x rows of candidate/kernel
+                // x rows of gates/kernel and candidate/kernel side by side: one N = 192 operand
+                pack_b_operand(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
                 pack_b_operand(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale);
                 pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale);
             }
@@ -854,9 +856,8 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
 template <int KX> struct GruFusedCfg {
     static constexpr int kChunks = KX / 16;                              // x K-chunks per step
     static constexpr int kStages = KX >= 128 ? 5 : 8;
-    static constexpr uint32_t kWgx = 0;                                  // {hi, lo} x [KX/8][128][8]
-    static constexpr uint32_t kWcx = kWgx + 2u * KX * 128 * 2;           // {hi, lo} x [KX/8][64][8]
-    static constexpr uint32_t kWgh = kWcx + 2u * KX * 64 * 2;            // {hi, lo} x [8][128][8]
+    static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
+    static constexpr uint32_t kWgh = kWx + 2u * KX * kNX * 2;            // {hi, lo} x [8][128][8]
     static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;           // {hi, lo} x [8][64][8]
     static constexpr uint32_t kWBytes = kWch + 2u * kH * 64 * 2;         // (KX + 64) * 192 * 4
     static constexpr uint32_t kHBuf = kWBytes;                           // {hi, lo} x [8][128][8]
@@ -945,6 +946,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
         if (lane == 0) {
             constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
             constexpr uint32_t idesc_c = make_idesc_bf16(128, kH);
+            constexpr uint32_t idesc_x = make_idesc_bf16(128, kNX);
             const uint32_t s0 = smem_u32(smem);
             const uint32_t hbuf = s0 + Cfg::kHBuf, ring = s0 + Cfg::kRing;
             uint32_t c = 0;                          // x chunks consumed so far
@@ -952,14 +954,12 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
             auto issue_x_chunk = [&](int kk, uint32_t buf) {
                 const int st = c % Cfg::kStages;
                 const uint32_t a0 = ring + st * 8192;
-                const uint32_t dg = tmem + buf * 256, dc = dg + 2 * kH;
+                const uint32_t dg = tmem + buf * 256;
 #pragma unroll
                 for (int pass = 0; pass < ((dbg & 2) ? 1 : 3); ++pass) {   // dbg & 2: timing experiment, single pass
                     const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
-                    const uint32_t wg = s0 + Cfg::kWgx + (pass == 2 ? (uint32_t)KX * 128 * 2 : 0u) + kk * 2 * (128 * 16);
-                    const uint32_t wc = s0 + Cfg::kWcx + (pass == 2 ? (uint32_t)KX * 64 * 2 : 0u) + kk * 2 * (64 * 16);
-                    umma_bf16(dg, ad, make_smem_desc(wg, 128 * 16, 128), idesc_g, (kk | pass) != 0);
-                    umma_bf16(dc, ad, make_smem_desc(wc, 64 * 16, 128), idesc_c, (kk | pass) != 0);
+                    const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
+                    umma_bf16(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0);   // gates | candidate
                 }
                 umma_commit(&empty[st]);
                 ++c;
@@ -1129,6 +1129,300 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
     if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
+// ====================================================================== TK4G: fused GRU layer, two tiles per CTA
+// Same mathematics as TK4F, restructured so that the tensor pipe never idles behind one chain's
+// serial MMA -> epilogue -> MMA dependency: a CTA runs TWO independent chains (two tiles of the
+// same direction, sharing the resident weights).  To make room for the second chain the state
+// operand h / r*h no longer lives in shared memory: the epilogue writes it (split bf16, packed)
+// into tensor memory with tcgen05.st and the state-part MMAs read A from TMEM (".ts" form).
+// TMEM per chain (256 columns): gates accumulator 0..127, candidate 128..191, A hi 192..223,
+// A lo 224..255.  Shared memory: weights (147 KB) + one 4-stage x ring per chain (64 KB).
+//   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
+//   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
+//   warp 18          : producer for both rings
+template <int KX> struct GruF2Cfg {
+    static constexpr int kChunks = KX / 16;
+    static constexpr int kStages = 4;
+    static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
+    static constexpr uint32_t kWgh = kWx + 2u * KX * kNX * 2;
+    static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;
+    static constexpr uint32_t kWBytes = kWch + 2u * kH * 64 * 2;
+    static constexpr uint32_t kRing = kWBytes;                            // [chain][stage] x 8 KB
+    static constexpr uint32_t kBias = kRing + 2u * kStages * 8192;
+    static constexpr uint32_t kBars = kBias + 192 * 4;
+    static constexpr uint32_t kSmem = kBars + 512;
+    // barrier indices inside a chain's group of 16
+    static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarFull = 5, kBarEmpty = 5 + kStages;
+};
+
+template <int KX>
+__global__ void __launch_bounds__(608, 1)
+tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
+                     const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
+                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles) {
+    using Cfg = GruF2Cfg<KX>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][16], then w_bar
+    uint64_t* w_bar = &bars[32];
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[33]);
+    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x & 1;
+    const int slot = blockIdx.x >> 1, n_slots = gridDim.x >> 1;
+    const int stride = 2 * n_slots;                        // tiles between consecutive tiles of one chain
+    auto tiles_of = [&](int chain) -> int {
+        const int first = slot * 2 + chain;
+        return first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+    };
+    auto blk_of = [&](int chain, int gs) -> size_t {
+        const int ti = gs / kWindow, s = gs - ti * kWindow;
+        return (size_t)(slot * 2 + chain + ti * stride) * kWindow + (dir ? kWindow - 1 - s : s);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 2; ++c) {
+            uint64_t* b = &bars[16 * c];
+            mbar_init(&b[Cfg::kBarG], 1);
+            mbar_init(&b[Cfg::kBarC], 1);
+            mbar_init(&b[Cfg::kBarRh], 8);
+            mbar_init(&b[Cfg::kBarH], 8);
+            mbar_init(&b[Cfg::kBarCfree], 8);
+            for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&b[Cfg::kBarFull + i], 1); mbar_init(&b[Cfg::kBarEmpty + i], 1); }
+        }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+    }
+    if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x];
+    if (warp == 16) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 18) {
+        // ------------------------------------------------------------ producer (both rings, polling)
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, Cfg::kWBytes);
+            const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
+            for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
+                const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
+                bulk_g2s(smem + off, wsrc + off, n, w_bar);
+            }
+            constexpr size_t plane = (size_t)128 * KX * 2;
+            constexpr int kAhead = 2;
+            const uint8_t* xbase = reinterpret_cast<const uint8_t*>(x_blocks);
+            int total[2] = {tiles_of(0) * kWindow, tiles_of(1) * kWindow};
+            int gs[2] = {0, 0}, kk[2] = {0, 0};
+            uint32_t cn[2] = {0, 0};
+            for (int c = 0; c < 2; ++c)
+                for (int a = 0; a < kAhead && a < total[c]; ++a) bulk_prefetch_l2(xbase + blk_of(c, a) * 2 * plane, 2 * plane);
+            while (gs[0] < total[0] || gs[1] < total[1]) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (gs[c] >= total[c]) continue;
+                    uint64_t* b = &bars[16 * c];
+                    const int st = cn[c] % Cfg::kStages;
+                    if (!mbar_test_wait(&b[Cfg::kBarEmpty + st], ((cn[c] / Cfg::kStages) & 1) ^ 1)) continue;
+                    const uint8_t* xb = xbase + blk_of(c, gs[c]) * 2 * plane;
+                    if (kk[c] == 0 && gs[c] + kAhead < total[c])
+                        bulk_prefetch_l2(xbase + blk_of(c, gs[c] + kAhead) * 2 * plane, 2 * plane);
+                    uint8_t* dst = smem + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
+                    mbar_expect_tx(&b[Cfg::kBarFull + st], 8192);
+                    bulk_g2s(dst, xb + kk[c] * 4096, 4096, &b[Cfg::kBarFull + st]);
+                    bulk_g2s(dst + 4096, xb + plane + kk[c] * 4096, 4096, &b[Cfg::kBarFull + st]);
+                    ++cn[c];
+                    if (++kk[c] == Cfg::kChunks) { kk[c] = 0; ++gs[c]; }
+                }
+            }
+        }
+    } else if (warp >= 16) {
+        // ------------------------------------------------------------ MMA issuer of chain (warp - 16)
+        if (lane == 0) {
+            constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
+            constexpr uint32_t idesc_c = make_idesc_bf16(128, kH);
+            constexpr uint32_t idesc_x = make_idesc_bf16(128, kNX);
+            const int c = warp - 16;
+            const uint32_t s0 = smem_u32(smem);
+            uint64_t* b = &bars[16 * c];
+            const uint32_t dg = tmem + c * 256, dc = dg + 2 * kH, ta = dg + 3 * kH;
+            const int total = tiles_of(c) * kWindow;
+            uint32_t cn = 0;
+            mbar_wait(w_bar, 0);
+            for (int gs = 0; gs < total; ++gs) {
+                const uint32_t par = gs & 1;
+                // x part: needs the previous step's accumulators drained
+                if (gs > 0) mbar_wait(&b[Cfg::kBarCfree], (gs - 1) & 1);
+                for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
+                    const int st = cn % Cfg::kStages;
+                    mbar_wait(&b[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t a0 = s0 + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
+                        const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
+                        umma_bf16(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0);
+                    }
+                    umma_commit(&b[Cfg::kBarEmpty + st]);
+                }
+                // state part of the gates
+                mbar_wait(&b[Cfg::kBarH], par);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
+                    const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
+#pragma unroll
+                    for (int kk = 0; kk < kH / 16; ++kk)
+                        umma_bf16_ts(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1);
+                }
+                umma_commit(&b[Cfg::kBarG]);
+                // state part of the candidate
+                mbar_wait(&b[Cfg::kBarRh], par);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
+                    const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
+#pragma unroll
+                    for (int kk = 0; kk < kH / 16; ++kk)
+                        umma_bf16_ts(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1);
+                }
+                umma_commit(&b[Cfg::kBarC]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int chain = warp >> 3;
+        const int q = warp & 3, hf = (warp >> 2) & 1;
+        const int row = q * 32 + lane;
+        const int j0 = hf * 32;
+        uint64_t* b = &bars[16 * chain];
+        const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + chain * 256 + j0;          // + gate * 64 + c0
+        const uint32_t t_ahi = tmem + ((uint32_t)(q * 32) << 16) + chain * 256 + 3 * kH + j0 / 2;   // + c0 / 2
+        const uint32_t t_alo = t_ahi + 32;
+        const float* hw = head_w ? head_w + dir * kH + j0 : nullptr;
+        const int my_tiles = tiles_of(chain);
+        float h[32], u[32];
+        int gs = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = 0.f;
+            {
+                const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                tmem_st8_u32(t_ahi, z);
+                tmem_st8_u32(t_ahi + 8, z);
+                tmem_st8_u32(t_alo, z);
+                tmem_st8_u32(t_alo + 8, z);
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
+            }
+            for (int s = 0; s < kWindow; ++s, ++gs) {
+                const uint32_t par = gs & 1;
+                const size_t blk = blk_of(chain, gs);
+                // ---- reset gate -> r*h operand
+                mbar_wait(&b[Cfg::kBarG], par);
+                tc_fence_after_sync();
+                {
+                    uint32_t ar[32];
+                    tmem_ld16_nowait(t_acc, ar);
+                    tmem_ld16_nowait(t_acc + 16, ar + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c0 = 0; c0 < 32; c0 += 16) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            float z[4], r[4];
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + c0 + i);
+                            z[0] = __uint_as_float(ar[c0 + i]) + b4.x; z[1] = __uint_as_float(ar[c0 + i + 1]) + b4.y;
+                            z[2] = __uint_as_float(ar[c0 + i + 2]) + b4.z; z[3] = __uint_as_float(ar[c0 + i + 3]) + b4.w;
+                            sigmoid4_z(z, r);
+                            split_bf16x2(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
+                            split_bf16x2(r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                        }
+                        tmem_st8_u32(t_ahi + c0 / 2, hi);
+                        tmem_st8_u32(t_alo + c0 / 2, lo);
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b[Cfg::kBarRh]);
+                // ---- update gate while the candidate MMA runs
+                {
+                    uint32_t au[32];
+                    tmem_ld16_nowait(t_acc + kH, au);
+                    tmem_ld16_nowait(t_acc + kH + 16, au + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float z[4];
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + kH + j0 + i);
+                        z[0] = __uint_as_float(au[i]) + b4.x; z[1] = __uint_as_float(au[i + 1]) + b4.y;
+                        z[2] = __uint_as_float(au[i + 2]) + b4.z; z[3] = __uint_as_float(au[i + 3]) + b4.w;
+                        sigmoid4_z(z, u + i);
+                    }
+                }
+                // ---- candidate, new state h = c + u (h - c)
+                mbar_wait(&b[Cfg::kBarC], par);
+                tc_fence_after_sync();
+                uint32_t ac[32];
+                tmem_ld16_nowait(t_acc + 2 * kH, ac);
+                tmem_ld16_nowait(t_acc + 2 * kH + 16, ac + 16);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b[Cfg::kBarCfree]);      // accumulators drained: next x part may start
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float z[4], cv[4];
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * kH + j0 + i);
+                    z[0] = __uint_as_float(ac[i]) + b4.x; z[1] = __uint_as_float(ac[i + 1]) + b4.y;
+                    z[2] = __uint_as_float(ac[i + 2]) + b4.z; z[3] = __uint_as_float(ac[i + 3]) + b4.w;
+                    tanh4_z(z, cv);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
+                    split_bf16x2(h[i], h[i + 1], hi[i >> 1], lo[i >> 1]);
+                    split_bf16x2(h[i + 2], h[i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                }
+                tmem_st8_u32(t_ahi, hi);
+                tmem_st8_u32(t_ahi + 8, hi + 8);
+                tmem_st8_u32(t_alo, lo);
+                tmem_st8_u32(t_alo + 8, lo + 8);
+                tmem_st_wait();
+                tc_fence_before_sync();
+                if (s + 1 < kWindow) {                   // hand h to the next step before the global stores
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
+                }
+                if (y_out) {
+                    // next layer's A operand: block {hi, lo} x [16][128][8], features dir*64 + j
+                    __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 8;
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {
+                        *reinterpret_cast<uint4*>(yb + kg * 128 * 8) = make_uint4(hi[4 * kg], hi[4 * kg + 1], hi[4 * kg + 2], hi[4 * kg + 3]);
+                        *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + kg * 128 * 8) = make_uint4(lo[4 * kg], lo[4 * kg + 1], lo[4 * kg + 2], lo[4 * kg + 3]);
+                    }
+                }
+                if (head_part) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc = fmaf(h[i], __ldg(hw + i), acc);
+                    head_part[((blk * 2 + dir) * 2 + hf) * 128 + row] = acc;
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc<512>(tmem);
+}
+
 // ====================================================================== TK5: head
 // p = sigmoid(part_fw + part_bw + b), scattered to sample order with the padding cut (infer.py:47).
 __global__ void tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const int64_t* __restrict__ src,
@@ -1178,6 +1472,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<128>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
@@ -1233,6 +1529,19 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     a_in = a0;
                 }
                 ProfScope ps(prof, KC_K4_GRU, stream);
+                if (e->fused_variant == 2) {
+                    const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
+                    if (L.in == kC)
+                        tc_gru_fused2_kernel<32><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                    else
+                        tc_gru_fused2_kernel<128><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                    CF_LAUNCHED();
+                    a_in = yo;
+                    head_parts = 4;
+                    continue;
+                }
                 const int grid = 2 * (int)std::min<int64_t>(tiles, e->n_sms / 2);
                 if (L.in == kC)
                     tc_gru_fused_kernel<32><<<grid, 576, GruFusedCfg<32>::kSmem, stream>>>(
