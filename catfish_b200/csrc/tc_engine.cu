@@ -88,6 +88,7 @@ struct TcEngine {
     int n_sms = 148;
     bool attr_done = false;
     int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
+    int x_depth = 2;                  // x chunks of one chain allowed in the tensor queue (CF_TC_XDEPTH)
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
 };
@@ -116,6 +117,7 @@ TcEngine* tc_create(const HostModel& hm) {
     e->simt = simt_create(hm);
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
     if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
+    if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(1, atoi(env));
     if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
@@ -1159,7 +1161,7 @@ template <int KX>
 __global__ void __launch_bounds__(608, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
-                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles) {
+                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth) {
     using Cfg = GruF2Cfg<KX>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][16], then w_bar
@@ -1255,6 +1257,13 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 if (gs > 0) mbar_wait(&b[Cfg::kBarCfree], (gs - 1) & 1);
                 for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
                     const int st = cn % Cfg::kStages;
+                    // keep the in-order tensor queue shallow (at most kXDepth x chunks of this chain in flight)
+                    // so that the other chain's state-part MMAs, which sit on its critical path, do not
+                    // wait behind a long run of x chunks: chunk cn - kXDepth must have completed
+                    if (cn >= (uint32_t)kXDepth) {
+                        const uint32_t pc = cn - kXDepth;
+                        mbar_wait(&b[Cfg::kBarEmpty + pc % Cfg::kStages], (pc / Cfg::kStages) & 1);
+                    }
                     mbar_wait(&b[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
                     tc_fence_after_sync();
                     const uint32_t a0 = s0 + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
@@ -1533,10 +1542,10 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
                     if (L.in == kC)
                         tc_gru_fused2_kernel<32><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth);
                     else
                         tc_gru_fused2_kernel<128><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles);
+                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth);
                     CF_LAUNCHED();
                     a_in = yo;
                     head_parts = 4;

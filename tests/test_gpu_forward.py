@@ -126,3 +126,47 @@ def test_engine_cross_check_large():
     assert worst < PROB_TOL, worst
     for a, b, sa, sb in zip(h1, h2, s1, s2):
         _check_intervals(a, sa, sb.astype(np.float64))
+
+
+@pytest.mark.parametrize("env", [{"CF_TC_FUSED": "1"}, {"CF_TC_UNFUSED": "1"}], ids=["one-tile-fused", "unfused-pair"])
+def test_tcgen05_kernel_variants(env, monkeypatch):
+    """The alternative GRU kernels of the tcgen05 engine (one tile per CTA; projection + recurrence
+    as two kernels) stay parity-green: they are the cross-checks of the default two-tile kernel."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = golden("forward_resnetrnn_shipped.npz")
+    m = _model("ResNetRNN", "auto")
+    if m.resolved_engine != "tcgen05":
+        pytest.skip("tcgen05 engine not available")
+    reads = [g["read%d" % i] for i in range(int(g["n_reads"]))] + synth.synth_reads([30000, 4481], base_seed=77)
+    hps, lengths, scores = infer.infer_reads(reads, m, return_scores=True)
+    ref = _model("ResNetRNN", "simt")
+    hps2, lengths2, scores2 = infer.infer_reads(reads, ref, return_scores=True)
+    assert lengths == lengths2
+    for a, b_, sa, sb in zip(hps, hps2, scores, scores2):
+        assert np.abs(sa - sb).max() < PROB_TOL
+        _check_intervals(a, sa, sb.astype(np.float64))
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a batch too large for the CPU oracle: batch invariance (a read's
+    result does not depend on its neighbours in the ragged batch), interval/probability consistency,
+    and determinism."""
+    m = _model("ResNetRNN", "auto")
+    reads = synth.synth_reads(synth.ragged_lengths(64, 50_000, 200_000, seed=11), base_seed=4000)
+    hps, lengths, scores = infer.infer_reads(reads, m, return_scores=True)
+    hps_again, _, scores_again = infer.infer_reads(reads, m, return_scores=True)
+    assert hps == hps_again
+    for a, b_ in zip(scores, scores_again):
+        np.testing.assert_array_equal(a, b_)                    # deterministic, bit for bit
+    # a permuted / partial batch gives every read the same answer (tiles are shared between reads)
+    order = [5, 63, 0, 17]
+    hps_p, len_p, scores_p = infer.infer_reads([reads[i] for i in order], m, return_scores=True)
+    for k, i in enumerate(order):
+        assert hps_p[k] == hps[i] and len_p[k] == lengths[i]
+        np.testing.assert_array_equal(scores_p[k], scores[i])
+    # intervals are exactly the post-processing of the returned probabilities
+    for h, s in zip(hps, scores):
+        labels = postprocess.correct_short(postprocess.class_from_threshold(s.astype(np.float64)))
+        assert h == postprocess.hp_in_pred(labels)
+        assert np.all((s >= 0) & (s <= 1))
