@@ -132,6 +132,8 @@ def cpu_run(weights, raw, offsets):
     """One pass of the reference path restated on the CPU over the given reads; returns seconds."""
     import torch
     from oracle import postprocess, tf_graph
+    if torch.get_num_threads() < (os.cpu_count() or 1):
+        torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use all host cores
     graph = tf_graph.TorchGraph(weights)
     t0 = time.perf_counter()
     n_int = 0

@@ -94,7 +94,8 @@ struct TcEngine {
 };
 
 bool tc_supported(const HostModel& hm) {
-    if (hm.desc.network_type == CF_NET_RESNET) return false;          // no GEMM-shaped GRU part
+    if (hm.desc.network_type == CF_NET_RESNET)                        // conv stack (TK2) + dense 32 -> 1
+        return hm.desc.layer_size_res == kC && hm.desc.n_layers_res >= 1 && hm.desc.n_layers_res <= 2;
     if (hm.desc.layer_size != kH) return false;
     if (hm.desc.network_type == CF_NET_RESNET_RNN && hm.desc.layer_size_res != kC) return false;
     return true;
@@ -1457,6 +1458,43 @@ __global__ void tc_head_kernel(const float* __restrict__ head_part, int n_parts,
     probs[src[g] + t] = p;
 }
 
+// ResNet-only head (resnet_class.py:23 commented out): dense 32 -> 1 + sigmoid straight from the
+// conv stack's output blocks ({hi, lo} x [4][128][8] bf16 per block), scattered to sample order.
+__global__ void tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ w, float b,
+                                    const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
+                                    const int32_t* __restrict__ read, const double* __restrict__ stats,
+                                    int64_t tile0, int64_t n_rows, float* __restrict__ probs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, w, t) with t fastest
+    if (i >= n_rows) return;
+    const int t = (int)(i % kWindow);
+    const int64_t wi = i / kWindow;
+    const int wr = (int)(wi % kTileWindows);
+    const int64_t tile = wi / kTileWindows;
+    const int64_t g = (tile0 + tile) * kTileWindows + wr;
+    if (t >= valid[g]) return;
+    const __nv_bfloat16* blk = y + ((size_t)tile * kWindow + t) * (2 * 128 * kC);
+    float acc = b;
+#pragma unroll
+    for (int kg = 0; kg < kC / 8; ++kg) {
+        const uint4 hi = *reinterpret_cast<const uint4*>(blk + ((size_t)kg * 128 + wr) * 8);
+        const uint4 lo = *reinterpret_cast<const uint4*>(blk + 128 * kC + ((size_t)kg * 128 + wr) * 8);
+        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float v0 = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+            const float v1 = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+            acc = fmaf(v0, __ldg(w + kg * 8 + 2 * k), acc);
+            acc = fmaf(v1, __ldg(w + kg * 8 + 2 * k + 1), acc);
+        }
+    }
+    float p = 1.f / (1.f + expf(-acc));
+    if (stats) {
+        const double sc = stats[2 * read[g] + 1];
+        if (!(sc > 0.0)) p = nanf("");
+    }
+    probs[src[g] + t] = p;
+}
+
 // ====================================================================== forward
 int simt_conv_stack(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats, const float* xwin,
                     WindowTable tab, int64_t tile0, int64_t tiles, int64_t chunk_tiles, const float** feat,
@@ -1595,7 +1633,13 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 a_in = yo;
             }
         }
-        {
+        if (n_layers == 0) {
+            // ResNet-only: dense on the conv output
+            ProfScope ps(prof, KC_K5_HEAD, stream);
+            tc_head_conv_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
+                a_in, e->head_w, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);
+            CF_LAUNCHED();
+        } else {
             ProfScope ps(prof, KC_K5_HEAD, stream);
             tc_head_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
                 head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);

@@ -265,6 +265,22 @@ __device__ __forceinline__ void tanh4(const float* x, float* y) {
 // (sigmoid) or by 2 log2(e) (tanh) when the weights were packed: one instruction less per value.
 //   sigmoid(x) = 1 / (1 + 2^z),      z = -x log2 e
 //   tanh(x)    = 1 - 2 / (1 + 2^z),  z = 2 x log2 e     (absolute error ~1e-7 near 0)
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#ifdef CF_FAST_ACT
+// Experiment: MUFU.TANH based activations (1 MUFU each, relative error ~2^-11).
+__device__ __forceinline__ void sigmoid4_z(const float* z, float* y) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = fmaf(tanh_approx(z[i] * -0.34657359027997264f), 0.5f, 0.5f);
+}
+__device__ __forceinline__ void tanh4_z(const float* z, float* y) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = tanh_approx(z[i] * 0.34657359027997264f);
+}
+#else
 __device__ __forceinline__ void sigmoid4_z(const float* z, float* y) {
     float a[4];
 #pragma unroll
@@ -279,6 +295,7 @@ __device__ __forceinline__ void tanh4_z(const float* z, float* y) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) y[i] = fmaf(-2.f, inv[i], 1.f);
 }
+#endif
 
 }  // namespace ptx
 }  // namespace cf
