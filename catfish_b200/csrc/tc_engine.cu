@@ -88,6 +88,7 @@ struct TcEngine {
     int n_sms = 148;
     bool attr_done = false;
     int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
+    int conv_variant = 2;             // 2 = one round per position (tc_conv2_kernel); 1 = three rounds (CF_TC_CONV=1)
     int x_depth = 2;                  // x chunks of one chain allowed in the tensor queue (CF_TC_XDEPTH)
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
@@ -118,6 +119,7 @@ TcEngine* tc_create(const HostModel& hm) {
     e->simt = simt_create(hm);
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
     if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
+    if (const char* env = getenv("CF_TC_CONV")) e->conv_variant = atoi(env) == 1 ? 1 : 2;
     if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(1, atoi(env));
     if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
@@ -458,6 +460,215 @@ tc_conv_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ r
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// ====================================================================== TK2 v2: deeper skew, one round per position
+// Same mathematics and operand layouts as tc_conv_kernel; the five MMA stages of the two residual
+// blocks are skewed over time so that ALL of them are issued in one batch per iteration u:
+//   o2[u-1], o3[u-2], [sc1|p1][u-3], p2[u-5], p3[u-6]
+// followed by ONE epilogue pass that consumes the five accumulators (all TMEM loads in flight at
+// once), writes the next operands, and computes o1[u+1] on CUDA cores.  One commit + one
+// "operands ready" barrier per iteration instead of three block-wide rounds.
+//   warps 0-7 : epilogue; thread = (window, 16 of the 32 channels)
+//   warp 8    : MMA issuer (warp-converged issue, elected lane)
+// TMEM: o2 0, o3 32, p2 64, p3 96, [sc1|p1] ring of 4 at 128 + 64 k (sc1 is read 3 iterations later).
+__device__ __forceinline__ void store_a_row16(uint8_t* slice, int row, int c0, const float* v) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1], hi[i], lo[i]);
+        uint8_t* dst = slice + (c0 / 8 + g) * 2048 + row * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void conv_mma_pred(uint32_t tmem_d, uint32_t a_slice, uint32_t w_mat, bool first, uint32_t elected) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, N);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ap = a_slice + (pass == 1 ? 8192u : 0u);
+        const uint32_t wp = w_mat + (pass == 2 ? (uint32_t)(kC * N * 2) : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+            umma_bf16_pred(tmem_d, make_smem_desc(ap + kk * 4096, 2048, 128), make_smem_desc(wp + kk * 2 * (N * 16), N * 16, 128),
+                           idesc, !(first && pass == 0 && kk == 0), elected);
+    }
+}
+
+template <int NRES>
+__global__ void __launch_bounds__(288, 1)
+tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
+                const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
+                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* prm = smem;
+    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 3 slices
+    uint8_t* o2 = o1 + 3 * kSliceBytes;
+    uint8_t* y0 = o2 + kSliceBytes;
+    uint8_t* p1 = y0 + kSliceBytes;                   // ring of 3 slices
+    uint8_t* p2 = p1 + 3 * kSliceBytes;
+    float* xs = reinterpret_cast<float*>(p2 + kSliceBytes);      // [35][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 35 * 128); // bar_ready, bar_mma, bar_prm
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const float* fp = reinterpret_cast<const float*>(prm);
+    uint64_t* bar_ready = &bars[0];
+    uint64_t* bar_mma = &bars[1];
+    uint64_t* bar_prm = &bars[2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_ready, 8);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_prm, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar_prm, ConvParams::kBytes);
+        bulk_g2s(prm, params, ConvParams::kBytes, bar_prm);
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    constexpr int kLastU = NRES == 2 ? kWindow + 5 : kWindow + 1;      // p3[34] at u = 40, o3[34] at u = 36
+    mbar_wait(bar_prm, 0);
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ issuer (all lanes converged)
+        const uint32_t elected = elect_one();
+        const uint32_t prm_u = smem_u32(prm);
+        const uint32_t o1_u = smem_u32(o1), o2_u = smem_u32(o2), y0_u = smem_u32(y0), p1_u = smem_u32(p1), p2_u = smem_u32(p2);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int u = 0; u <= kLastU; ++u, ++it) {
+                mbar_wait(bar_ready, it & 1);
+                tc_fence_after_sync();
+                const int t1 = u - 1, t2 = u - 2, t3 = u - 3, t4 = u - 5, t5 = u - 6;
+                if (t1 >= 0 && t1 < kWindow) {
+                    bool first = true;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = t1 + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma_pred<32>(tmem + 0, o1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
+                        first = false;
+                    }
+                }
+                if (t2 >= 0 && t2 < kWindow) conv_mma_pred<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
+                if (NRES == 2) {
+                    if (t3 >= 0 && t3 < kWindow)
+                        conv_mma_pred<64>(tmem + 128 + (t3 & 3) * 64, y0_u, prm_u + ConvParams::kW45, true, elected);
+                    if (t4 >= 0 && t4 < kWindow) {
+                        bool first = true;
+#pragma unroll
+                        for (int tap = 0; tap < 3; ++tap) {
+                            const int tt = t4 + tap - 1;
+                            if (tt < 0 || tt >= kWindow) continue;
+                            conv_mma_pred<32>(tmem + 64, p1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
+                            first = false;
+                        }
+                    }
+                    if (t5 >= 0 && t5 < kWindow) conv_mma_pred<32>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
+                }
+                umma_commit_pred(bar_mma, elected);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const int c0 = ch * 16;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + c0;
+        auto relu_bias = [&](uint32_t* r, int slot, float* v) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(fp + 32 * slot + c0 + i);
+                v[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
+                v[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
+                v[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
+                v[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+            }
+        };
+        auto make_o1 = [&](int t) {               // o1[t] = relu(x a1 + b1) on CUDA cores
+            const float x = xs[t * 128 + row];
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
+            store_a_row16(o1 + (t % 3) * kSliceBytes, row, c0, v);
+        };
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // ---- gather + normalise (infer.py:101-105, 32-38): the two threads of a window split its 35 samples
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of xs are done
+            {
+                const int64_t g = (tile0 + tile) * kTileWindows + row;
+                const int nv = valid[g];
+                const int64_t s0 = src[g];
+                double shift = 0.0, scale = 1.0;
+                if (raw && nv > 0) { const int r = read[g]; shift = stats[2 * r]; scale = stats[2 * r + 1]; }
+                const int tb = ch ? 18 : 0, te = ch ? kWindow : 18;
+                for (int t = tb; t < te; ++t) {
+                    float v = 0.f;
+                    if (t < nv) v = raw ? (float)(((double)raw[s0 + t] - shift) / scale) : xwin[s0 + t];
+                    xs[t * 128 + row] = v;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            make_o1(0);
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ready);
+            for (int u = 0; u <= kLastU; ++u, ++it) {
+                const int t1 = u - 1, t2 = u - 2, t3 = u - 3, t4 = u - 5, t5 = u - 6;
+                const bool h1 = t1 >= 0 && t1 < kWindow, h2 = t2 >= 0 && t2 < kWindow;
+                const bool h3 = NRES == 2 && t3 >= 0 && t3 < kWindow, h4 = NRES == 2 && t4 >= 0 && t4 < kWindow;
+                const bool h5 = NRES == 2 && t5 >= 0 && t5 < kWindow;
+                mbar_wait(bar_mma, it & 1);
+                tc_fence_after_sync();
+                uint32_t r1[16], r2[16], r3[16], r4[16], r5[16], rs[16];
+                if (h1) tmem_ld16_nowait(t_lane + 0, r1);
+                if (h2) tmem_ld16_nowait(t_lane + 32, r2);
+                if (h3) tmem_ld16_nowait(t_lane + 128 + (t3 & 3) * 64 + 32, r3);
+                if (h4) tmem_ld16_nowait(t_lane + 64, r4);
+                if (h5) {
+                    tmem_ld16_nowait(t_lane + 96, r5);
+                    tmem_ld16_nowait(t_lane + 128 + (t5 & 3) * 64, rs);
+                }
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                float v[16];
+                if (h1) { relu_bias(r1, 4, v); store_a_row16(o2, row, c0, v); }                  // b2
+                if (h2) {
+                    relu_bias(r2, 5, v);                                                         // b3
+                    const float x = xs[t2 * 128 + row];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
+                    if (NRES == 2) store_a_row16(y0, row, c0, v);
+                    else store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t2) * kSliceBytes, row, c0, v);
+                }
+                if (h3) { relu_bias(r3, 7, v); store_a_row16(p1 + (t3 % 3) * kSliceBytes, row, c0, v); }   // b5
+                if (h4) { relu_bias(r4, 8, v); store_a_row16(p2, row, c0, v); }                  // b6
+                if (h5) {
+                    relu_bias(r5, 9, v);                                                         // b7
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + (__uint_as_float(rs[i]) + fp[192 + c0 + i]), 0.f);   // + sc1 + b4
+                    store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
+                }
+                if (u + 1 < kWindow) make_o1(u + 1);
+                if (u < kLastU) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ready);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 // ====================================================================== TK3: input projection
@@ -1521,6 +1732,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
@@ -1550,7 +1763,14 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         if (e->conv_params) {
             ProfScope ps(prof, KC_K2_CONV, stream);
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
-            if (e->conv_nres == 2)
+            if (e->conv_variant == 2) {
+                if (e->conv_nres == 2)
+                    tc_conv2_kernel<2><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                         tab.read, tile0, (int)tiles, a0);
+                else
+                    tc_conv2_kernel<1><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                         tab.read, tile0, (int)tiles, a0);
+            } else if (e->conv_nres == 2)
                 tc_conv_kernel<2><<<grid, 128, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                     tab.read, tile0, (int)tiles, a0);
             else

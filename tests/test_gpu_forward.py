@@ -128,7 +128,8 @@ def test_engine_cross_check_large():
         _check_intervals(a, sa, sb.astype(np.float64))
 
 
-@pytest.mark.parametrize("env", [{"CF_TC_FUSED": "1"}, {"CF_TC_UNFUSED": "1"}], ids=["one-tile-fused", "unfused-pair"])
+@pytest.mark.parametrize("env", [{"CF_TC_FUSED": "1"}, {"CF_TC_UNFUSED": "1"}, {"CF_TC_CONV": "1"}],
+                         ids=["one-tile-fused", "unfused-pair", "three-round-conv"])
 def test_tcgen05_kernel_variants(env, monkeypatch):
     """The alternative GRU kernels of the tcgen05 engine (one tile per CTA; projection + recurrence
     as two kernels) stay parity-green: they are the cross-checks of the default two-tile kernel."""
