@@ -376,7 +376,7 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
     }
     CF_TRY(engine_forward(m, raw0, m->stats.as<double>(), nullptr, tab, plan.n_tiles, probs, stream));
     {
-        ProfScope ps(&m->prof, KC_K6_INTERVALS, stream, 6);
+        ProfScope ps(&m->prof, KC_K6_INTERVALS, stream, 7);
         CF_TRY(k6_call_intervals(m->k6, probs, BITS_FROM_F32, threshold, 1, offsets_dev, n_reads,
                                  plan.total_samples, intervals_dev, interval_offsets_dev, nullptr, capacity,
                                  min_run, ext_left, ext_right, stream));
@@ -387,6 +387,24 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
 }  // namespace cf
 
 // ================================================================== extern "C"
+// ---------------------------------------------------------------- model-free helpers
+namespace {
+struct TempBufs {
+    std::vector<cf::DevBuf*> bufs;
+    ~TempBufs() { for (auto* b : bufs) { b->release(); delete b; } }
+    cf::DevBuf* make() { bufs.push_back(new cf::DevBuf()); return bufs.back(); }
+};
+
+int upload_offsets(const int64_t* offsets_host, int32_t n_reads, cf::DevBuf* buf, cudaStream_t st) {
+    CF_TRY(buf->ensure(sizeof(int64_t) * ((size_t)n_reads + 1)));
+    std::vector<int64_t> off((size_t)n_reads + 1);
+    for (int32_t i = 0; i <= n_reads; ++i) off[i] = offsets_host[i] - offsets_host[0];
+    CF_CUDA(cudaMemcpyAsync(buf->ptr, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, st));
+    CF_CUDA(cudaStreamSynchronize(st));     // `off` is pageable and about to go out of scope
+    return CF_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int cf_abi_version(void) { return CF_ABI_VERSION; }
@@ -396,6 +414,39 @@ int cf_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int cf_merge_chunks(int32_t device, const int64_t* intervals_dev, const int64_t* interval_offsets_host,
+                    const int64_t* read_lengths_host, int32_t n_reads, int64_t chunk_size, int64_t* merged_dev,
+                    int64_t* merged_count_dev, int64_t* nonhp_dev, int64_t* nonhp_count_dev, void* stream) {
+    if (n_reads < 0 || !interval_offsets_host || !read_lengths_host || !merged_dev || !merged_count_dev || !nonhp_dev ||
+        !nonhp_count_dev) {
+        cf::set_error("cf_merge_chunks: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    if (n_reads == 0) return CF_OK;
+    CF_TRY(cf::use_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n_int = interval_offsets_host[n_reads] - interval_offsets_host[0];
+    if (n_int < 0 || (n_int > 0 && !intervals_dev)) { cf::set_error("cf_merge_chunks: bad offsets"); return CF_ERR_BAD_ARG; }
+    TempBufs tmp;
+    cf::DevBuf* work = tmp.make();
+    cf::DevBuf* idx = tmp.make();
+    cf::DevBuf* meta = tmp.make();
+    CF_TRY(work->ensure(sizeof(int64_t) * 2 * (size_t)(n_int + 1)));
+    CF_TRY(idx->ensure(sizeof(int32_t) * (size_t)(n_int + n_reads + 1)));
+    CF_TRY(meta->ensure(sizeof(int64_t) * (2 * (size_t)n_reads + 1)));
+    std::vector<int64_t> host((size_t)2 * n_reads + 1);
+    for (int32_t r = 0; r <= n_reads; ++r) host[r] = interval_offsets_host[r] - interval_offsets_host[0];
+    for (int32_t r = 0; r < n_reads; ++r) host[n_reads + 1 + r] = read_lengths_host[r];
+    CF_CUDA(cudaMemcpyAsync(meta->ptr, host.data(), sizeof(int64_t) * host.size(), cudaMemcpyHostToDevice, st));
+    if (n_int > 0)
+        CF_CUDA(cudaMemcpyAsync(work->ptr, intervals_dev + 2 * interval_offsets_host[0], sizeof(int64_t) * 2 * (size_t)n_int,
+                                cudaMemcpyDeviceToDevice, st));
+    int s = cf::k7_merge_chunks(work->as<int64_t>(), meta->as<int64_t>(), meta->as<int64_t>() + n_reads + 1, n_reads,
+                                chunk_size, idx->as<int32_t>(), merged_dev, merged_count_dev, nonhp_dev, nonhp_count_dev, st);
+    cudaStreamSynchronize(st);
+    return s;
 }
 
 int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int32_t k, const float* wx_host,
@@ -607,23 +658,6 @@ int cf_infer_reads_host(cf_model* m, const int16_t* raw_host, const int64_t* off
     return CF_OK;
 }
 
-// ---------------------------------------------------------------- model-free helpers
-namespace {
-struct TempBufs {
-    std::vector<cf::DevBuf*> bufs;
-    ~TempBufs() { for (auto* b : bufs) { b->release(); delete b; } }
-    cf::DevBuf* make() { bufs.push_back(new cf::DevBuf()); return bufs.back(); }
-};
-
-int upload_offsets(const int64_t* offsets_host, int32_t n_reads, cf::DevBuf* buf, cudaStream_t st) {
-    CF_TRY(buf->ensure(sizeof(int64_t) * ((size_t)n_reads + 1)));
-    std::vector<int64_t> off((size_t)n_reads + 1);
-    for (int32_t i = 0; i <= n_reads; ++i) off[i] = offsets_host[i] - offsets_host[0];
-    CF_CUDA(cudaMemcpyAsync(buf->ptr, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, st));
-    CF_CUDA(cudaStreamSynchronize(st));     // `off` is pageable and about to go out of scope
-    return CF_OK;
-}
-}  // namespace
 
 int cf_normalize_reads(int32_t device, const int16_t* raw_dev, const int64_t* offsets_host, int32_t n_reads,
                        double* stats_dev, double* norm_dev, void* stream) {

@@ -158,4 +158,9 @@ int k6_class_from_threshold(const double* scores, int64_t n, double threshold, i
 int k6_correct_short(const int64_t* labels, int64_t n, int32_t threshold, int64_t* out,
                      cudaStream_t stream);
 
+// ---------------------------------------------------------------- k7: chunk merging (next row N1)
+int k7_merge_chunks(int64_t* work, const int64_t* ioff, const int64_t* read_len, int n_reads, int64_t chunk,
+                    int32_t* idx, int64_t* merged, int64_t* merged_cnt, int64_t* nonhp, int64_t* nonhp_cnt,
+                    cudaStream_t stream);
+
 }  // namespace cf

@@ -76,35 +76,67 @@ __global__ void k6_pack_kernel(const typename Src<SRC>::T* __restrict__ vals, in
     }
 }
 
-// f32 fast path: each lane loads 4 consecutive probabilities (128-bit), 8 lanes form a word.
-__global__ void k6_pack_f32x4_kernel(const float* __restrict__ vals, int64_t n, double thr,
-                                     int64_t n_words, const unsigned* __restrict__ bwords,
-                                     unsigned* __restrict__ lwords, unsigned* __restrict__ swords) {
+// f32 fast path: each lane loads 4 consecutive probabilities (128-bit), 8 lanes form a word; four
+// independent 128-sample groups per warp iteration keep 4 loads per thread in flight (HBM-bound).
+__global__ void __launch_bounds__(256)
+k6_pack_f32x4_kernel(const float* __restrict__ vals, int64_t n, double thr,
+                     int64_t n_words, const unsigned* __restrict__ bwords,
+                     unsigned* __restrict__ lwords, unsigned* __restrict__ swords) {
+    constexpr int kUnroll = 4;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t n_groups = (n_words + 3) >> 2;           // 128 samples per warp iteration
-    for (int64_t g = warp; g < n_groups; g += n_warps) {
-        const int64_t i = (g << 7) + (lane << 2);
-        unsigned nib = 0;
-        if (i + 3 < n) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(vals + i));
-            nib = ((double)v.x >= thr ? 1u : 0u) | ((double)v.y >= thr ? 2u : 0u) |
-                  ((double)v.z >= thr ? 4u : 0u) | ((double)v.w >= thr ? 8u : 0u);
-        } else {
-            for (int k = 0; k < 4; ++k)
-                if (i + k < n && (double)vals[i + k] >= thr) nib |= 1u << k;
+    const int64_t n_groups = (n_words + 3) >> 2;           // 128 samples per group
+    const float thr_f = (float)thr;
+    const bool thr_exact = (double)thr_f == thr;           // then the fp32 compare equals the fp64 one
+    for (int64_t g0 = warp * kUnroll; g0 < n_groups; g0 += n_warps * kUnroll) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            const int64_t i = ((g0 + k) << 7) + (lane << 2);
+            v[k] = make_float4(-1.f, -1.f, -1.f, -1.f);
+            if (i + 3 < n) {
+                v[k] = __ldcs(reinterpret_cast<const float4*>(vals + i));
+            } else if (i < n) {
+                float t[4] = {-1.f, -1.f, -1.f, -1.f};
+                for (int j = 0; j < 4; ++j)
+                    if (i + j < n) t[j] = vals[i + j];
+                v[k] = make_float4(t[0], t[1], t[2], t[3]);
+            }
         }
-        unsigned L = nib << ((lane & 7) << 2);
-        L |= __shfl_xor_sync(0xffffffffu, L, 1);
-        L |= __shfl_xor_sync(0xffffffffu, L, 2);
-        L |= __shfl_xor_sync(0xffffffffu, L, 4);
-        const int64_t w = (g << 2) + (lane >> 3);
-        if ((lane & 7) == 0 && w < n_words) {
-            unsigned carry = 0;
-            if (w > 0) carry = (double)vals[(w << 5) - 1] >= thr ? 1u : 0u;
-            lwords[w] = L;
-            swords[w] = L & (~((L << 1) | carry) | bwords[w]);
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            const int64_t g = g0 + k;
+            if (g >= n_groups) break;
+            const int64_t i = (g << 7) + (lane << 2);
+            unsigned nib;
+            if (thr_exact) {
+                nib = (v[k].x >= thr_f ? 1u : 0u) | (v[k].y >= thr_f ? 2u : 0u) | (v[k].z >= thr_f ? 4u : 0u) | (v[k].w >= thr_f ? 8u : 0u);
+            } else {
+                nib = ((double)v[k].x >= thr ? 1u : 0u) | ((double)v[k].y >= thr ? 2u : 0u) |
+                      ((double)v[k].z >= thr ? 4u : 0u) | ((double)v[k].w >= thr ? 8u : 0u);
+            }
+            // positions past the end were filled with -1: mask them for thresholds <= -1
+            if (i + 3 >= n) {
+                unsigned m = 0;
+                for (int j = 0; j < 4; ++j)
+                    if (i + j < n) m |= 1u << j;
+                nib &= m;
+            }
+            unsigned L = nib << ((lane & 7) << 2);
+            L |= __shfl_xor_sync(0xffffffffu, L, 1);
+            L |= __shfl_xor_sync(0xffffffffu, L, 2);
+            L |= __shfl_xor_sync(0xffffffffu, L, 4);
+            // carry = label of the sample before this word = top bit of the previous lane-group's word
+            unsigned prev = __shfl_up_sync(0xffffffffu, L, 8);
+            const int64_t w = (g << 2) + (lane >> 3);
+            if ((lane & 7) == 0 && w < n_words) {
+                unsigned carry;
+                if (lane >= 8) carry = prev >> 31;
+                else carry = w > 0 ? (((double)vals[(w << 5) - 1] >= thr) ? 1u : 0u) : 0u;
+                lwords[w] = L;
+                swords[w] = L & (~((L << 1) | carry) | bwords[w]);
+            }
         }
     }
 }
@@ -126,7 +158,7 @@ k6_runs_kernel(const unsigned* __restrict__ lwords, const unsigned* __restrict__
                const unsigned* __restrict__ bwords, int64_t n_words, const int64_t* __restrict__ offsets,
                int n_reads, int min_run, int ext_left, int ext_right,
                unsigned* __restrict__ block_cnt, const int64_t* __restrict__ block_base,
-               unsigned long long* __restrict__ read_cnt, int64_t* __restrict__ intervals,
+               int64_t* __restrict__ run_start_global, int64_t* __restrict__ intervals,
                int64_t capacity) {
     __shared__ unsigned warp_sums[kWordsPerBlock / 32];
     const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
@@ -169,12 +201,6 @@ k6_runs_kernel(const unsigned* __restrict__ lwords, const unsigned* __restrict__
     }
     if (!EMIT) {
         if (threadIdx.x == 0) block_cnt[blockIdx.x] = total;
-        int k = 0;
-        for (unsigned q = qual; q; q &= q - 1, ++k) {
-            const int eb = __ffs(q) - 1;
-            const int64_t s = k < 4 ? starts[k] : run_start(swords, w, eb);
-            atomicAdd(&read_cnt[find_read(offsets, n_reads, s)], 1ull);
-        }
     } else {
         int64_t rank = block_base[blockIdx.x] + base + inc - (unsigned)nq;
         int k = 0;
@@ -182,6 +208,7 @@ k6_runs_kernel(const unsigned* __restrict__ lwords, const unsigned* __restrict__
             const int eb = __ffs(q) - 1;
             const int64_t s = k < 4 ? starts[k] : run_start(swords, w, eb);
             const int64_t len = (w << 5) + eb - s + 1;
+            run_start_global[rank] = s;
             if (rank < capacity) {
                 const int64_t local = s - offsets[find_read(offsets, n_reads, s)];
                 intervals[2 * rank] = local - ext_left;
@@ -189,6 +216,24 @@ k6_runs_kernel(const unsigned* __restrict__ lwords, const unsigned* __restrict__
             }
         }
     }
+}
+
+// interval_offsets[r] = number of emitted runs that start before read r = lower bound of
+// offsets[r] in the (ascending) global run starts.  No atomics, any number of reads.
+__global__ void k6_read_offsets_kernel(const int64_t* __restrict__ run_start_global, const int64_t* __restrict__ total_runs,
+                                       const int64_t* __restrict__ offsets, int n_reads,
+                                       int64_t* __restrict__ interval_offsets, int64_t* __restrict__ total_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    const int64_t n = *total_runs;
+    const int64_t key = offsets[r];
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (run_start_global[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    interval_offsets[r] = lo;
+    if (r == n_reads && total_out) *total_out = n;
 }
 
 // ---------------------------------------------------------------- single-block exclusive scans
@@ -251,15 +296,17 @@ int k6_call_intervals(IntervalScratch& s, const void* values, int source, double
     CF_TRY(s.block_cnt.ensure(sizeof(unsigned) * (size_t)n_blocks + sizeof(int64_t) * (size_t)(n_blocks + 1) + 16));
     int64_t* block_base = s.block_cnt.as<int64_t>();
     unsigned* block_cnt = reinterpret_cast<unsigned*>(block_base + n_blocks + 1);
-    CF_TRY(s.read_cnt.ensure(sizeof(unsigned long long) * (size_t)n_reads));
-    unsigned long long* read_cnt = s.read_cnt.as<unsigned long long>();
+    // global start of every emitted run (ascending): at most one run per min_run + 1 samples
+    const int64_t max_runs = n / ((min_run < 1 ? 1 : min_run) + 1) + n_reads + 1;
+    CF_TRY(s.read_cnt.ensure(sizeof(int64_t) * (size_t)max_runs));
+    int64_t* run_start_global = s.read_cnt.as<int64_t>();
 
     CF_CUDA(cudaMemsetAsync(bwords, 0, sizeof(unsigned) * (size_t)(n_words + 1), stream));
-    CF_CUDA(cudaMemsetAsync(read_cnt, 0, sizeof(unsigned long long) * (size_t)n_reads, stream));
     k6_bounds_kernel<<<(unsigned)ceil_div(n_reads, 256), 256, 0, stream>>>(offsets_dev, n_reads, n, bwords);
     CF_LAUNCHED();
 
-    int64_t pack_blocks = ceil_div(n_words, 8);      // 8 warps per block
+    int64_t pack_blocks = ceil_div(n_words, 8 * 16);  // 8 warps per block, 16 words per warp iteration
+    if (pack_blocks < 1) pack_blocks = 1;
     if (pack_blocks > 148 * 8) pack_blocks = 148 * 8;
     if (source == BITS_FROM_F32) {
         if ((reinterpret_cast<uintptr_t>(values) & 15) == 0) {
@@ -280,15 +327,16 @@ int k6_call_intervals(IntervalScratch& s, const void* values, int source, double
 
     k6_runs_kernel<false><<<(unsigned)n_blocks, kWordsPerBlock, 0, stream>>>(
         lwords, swords, bwords, n_words, offsets_dev, n_reads, min_run, ext_left, ext_right,
-        block_cnt, nullptr, read_cnt, nullptr, 0);
+        block_cnt, nullptr, nullptr, nullptr, 0);
     CF_LAUNCHED();
     k6_scan_kernel<unsigned><<<1, 1024, 0, stream>>>(block_cnt, n_blocks, block_base, nullptr);
     CF_LAUNCHED();
-    k6_scan_kernel<unsigned long long><<<1, 1024, 0, stream>>>(read_cnt, n_reads, interval_offsets, total_out);
-    CF_LAUNCHED();
     k6_runs_kernel<true><<<(unsigned)n_blocks, kWordsPerBlock, 0, stream>>>(
         lwords, swords, bwords, n_words, offsets_dev, n_reads, min_run, ext_left, ext_right,
-        nullptr, block_base, nullptr, intervals, capacity);
+        nullptr, block_base, run_start_global, intervals, capacity);
+    CF_LAUNCHED();
+    k6_read_offsets_kernel<<<(unsigned)ceil_div(n_reads + 1, 256), 256, 0, stream>>>(
+        run_start_global, block_base + n_blocks, offsets_dev, n_reads, interval_offsets, total_out);
     CF_LAUNCHED();
     return CF_OK;
 }

@@ -187,6 +187,21 @@ const char* cf_profile_class_name(int32_t cls);
 int cf_profile_read(cf_model* model, double* ms_out, int64_t* launches_out, int32_t n);
 
 /*
+ * cf_merge_chunks - "next" row N1: replaces the chunk merging of the reference's CLI loop
+ * (catfish/catfish:58-81) and center_hp (catfish/catfish:121-135) for a batch of reads.
+ *   intervals_dev / interval_offsets_host : the CSR output of cf_infer_reads (offsets on the host)
+ *   read_lengths_host [n_reads]           : len_read of every read
+ *   merged_dev  int64 [(n_intervals + n_reads)][2] : read r's merged chunks start at row offsets[r] + r
+ *   nonhp_dev   int64 [(n_intervals + 2 n_reads)][2]: read r's non-HP ranges start at row offsets[r] + 2 r
+ *   merged_count_dev / nonhp_count_dev int64 [n_reads]; nonhp_count -1 marks a read without any
+ *   interval (the reference then stores the single odd entry [((0, len_read), len_read)], :81).
+ * Reproduces the reference's list aliasing and the `i - 1` wrap-around at i == 0.  Synchronises.
+ */
+int cf_merge_chunks(int32_t device, const int64_t* intervals_dev, const int64_t* interval_offsets_host,
+                    const int64_t* read_lengths_host, int32_t n_reads, int64_t chunk_size, int64_t* merged_dev,
+                    int64_t* merged_count_dev, int64_t* nonhp_dev, int64_t* nonhp_count_dev, void* stream);
+
+/*
  * cf_selftest_xproj - unit self-test of the tcgen05 GEMM path (no reference counterpart): the GRU
  * input projection out[blk][n][w] = sum_k a[blk*128 + w][k] * wx[k][n] + bias[n], n in [0, 384),
  * through the engine's operand packing, bulk (TMA) copies, tcgen05.mma and TMEM epilogue.

@@ -1,0 +1,56 @@
+"""Chunk merging (next row N1): oracle pinned by the reference's own source lines; GPU kernel vs both."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+from oracle import chunks as ochunks
+
+
+def _cases():
+    with open(os.path.join(GOLDEN, "chunks.json")) as f:
+        return json.load(f)
+
+
+def _norm(x):
+    return json.loads(json.dumps(x))
+
+
+def _random_intervals(rng, len_read):
+    out, pos = [], int(rng.integers(-11, 200))
+    while pos < len_read - 30 and len(out) < 400:
+        n = int(rng.integers(15, 400))
+        out.append([pos - 11, pos + n + 16])
+        pos += n + int(rng.integers(1, 1500))
+    return out
+
+
+def test_oracle_matches_reference_lines():
+    for c in _cases():
+        merged, nonhp = ochunks.merge_read(c["hp_positions"], c["len_read"], c["chunk_size"])
+        assert merged == c["merged"] and _norm(nonhp) == c["nonhp"]
+
+
+@pytest.mark.gpu
+def test_gpu_merge_matches_golden_and_oracle():
+    from catfish_b200 import chunks
+    cases = _cases()
+    for chunk in (1000, 300):
+        sel = [c for c in cases if c["chunk_size"] == chunk]
+        hp, non = chunks.merge_reads([c["hp_positions"] for c in sel], [c["len_read"] for c in sel], chunk)
+        for c, h, n in zip(sel, hp, non):
+            assert h == c["merged"] and _norm(n) == c["nonhp"]
+    rng = np.random.default_rng(8)
+    lens = [int(rng.integers(200, 60000)) for _ in range(300)]
+    ivs = [_random_intervals(rng, n) if i % 11 else [] for i, n in enumerate(lens)]
+    for chunk in (1000, 100, 5000):
+        hp, non = chunks.merge_reads(ivs, lens, chunk)
+        for iv, n, h, x in zip(ivs, lens, hp, non):
+            want_h, want_n = ochunks.merge_read(iv, n, chunk)
+            assert h == want_h and _norm(x) == _norm(want_n)
+    h1, n1 = chunks.merge_read([[-11, 46]], 500)
+    assert (h1, n1) == ochunks.merge_read([[-11, 46]], 500)
+    m = [[10, 50]]
+    assert chunks.center_hp(m, 2000, 1000) == ochunks.center_hp([[10, 50]], 2000, 1000)

@@ -109,6 +109,31 @@ def main():
         np.savez_compressed(os.path.join(OUT, "forward_%s_seed%d.npz" % (tag, seed)),
                             x=x, p64=p64, seed=np.array(seed), kind=np.array(kind),
                             **{"hpm_" + k: np.array(v) for k, v in hpm.items()})
+    # ---- chunk merging (next row N1): execute the reference CLI's own source lines (catfish/catfish:58-81, 121-135)
+    import copy
+    import json
+    import textwrap
+    src = open("/root/reference/catfish/catfish").read().splitlines()
+    body = textwrap.dedent("\n".join(src[57:81]))                 # lines 58-81: the per-file merge block
+    center = "\n".join(src[120:135])                              # lines 121-135: def center_hp
+    cases = []
+    graph_reads = synth.synth_reads([30000, 12000, 4000, 700, 1225], base_seed=600)
+    case_inputs = []
+    for r in graph_reads:
+        hps, n, _ = postprocess.infer_read(r, torch_graph.infer)
+        case_inputs.append((hps, n))
+    case_inputs += [([], 5000), ([[-11, 46]], 500), ([[-11, 1200]], 3000), ([[100, 160], [150, 210], [2000, 2100]], 2500),
+                    ([[5, 40], [30, 1300], [1290, 1400], [4000, 4100]], 4200), ([[2400, 2480]], 2500), ([[0, 10]], 200)]
+    for chunk in (1000, 300):
+        for hps, n in case_inputs:
+            ns = {"hp_positions": copy.deepcopy(hps), "len_read": n, "chunk_size": chunk, "hp_dict": {}, "nonhp_dict": {},
+                  "fast5_file": "f"}
+            exec(center, ns)
+            exec(body, ns)
+            cases.append({"hp_positions": hps, "len_read": n, "chunk_size": chunk,
+                          "merged": ns["hp_dict"].get("f"), "nonhp": json.loads(json.dumps(ns["nonhp_dict"]["f"]))})
+    with open(os.path.join(OUT, "chunks.json"), "w") as f:
+        json.dump(cases, f)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
