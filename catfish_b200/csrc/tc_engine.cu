@@ -89,6 +89,7 @@ struct TcEngine {
     bool attr_done = false;
     int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
     int conv_variant = 2;             // 2 = one round per position (tc_conv2_kernel); 1 = three rounds (CF_TC_CONV=1)
+    bool trace_done = false;
     int x_depth = 2;                  // x chunks of one chain allowed in the tensor queue (CF_TC_XDEPTH)
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
@@ -1350,13 +1351,13 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
 // operand h / r*h no longer lives in shared memory: the epilogue writes it (split bf16, packed)
 // into tensor memory with tcgen05.st and the state-part MMAs read A from TMEM (".ts" form).
 // TMEM per chain (256 columns): gates accumulator 0..127, candidate 128..191, A hi 192..223,
-// A lo 224..255.  Shared memory: weights (147 KB) + one 4-stage x ring per chain (64 KB).
+// A lo 224..255.  Shared memory: weights (147 KB) + one 5-stage x ring per chain (80 KB).
 //   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
 //   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
-//   warp 18          : producer for both rings
+//   warp 18 / 19     : producer of chain 0 / 1 (weights once, then the chain's x ring)
 template <int KX> struct GruF2Cfg {
     static constexpr int kChunks = KX / 16;
-    static constexpr int kStages = 4;
+    static constexpr int kStages = 5;
     static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
     static constexpr uint32_t kWgh = kWx + 2u * KX * kNX * 2;
     static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;
@@ -1365,16 +1366,29 @@ template <int KX> struct GruF2Cfg {
     static constexpr uint32_t kBias = kRing + 2u * kStages * 8192;
     static constexpr uint32_t kBars = kBias + 192 * 4;
     static constexpr uint32_t kSmem = kBars + 512;
-    // barrier indices inside a chain's group of 16
+    // barrier indices inside a chain's group of 16 (5 + 2 * kStages <= 16)
     static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarFull = 5, kBarEmpty = 5 + kStages;
 };
 
 template <int KX>
-__global__ void __launch_bounds__(608, 1)
+__global__ void __launch_bounds__(640, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
-                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth) {
+                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth,
+                     long long* __restrict__ trace) {
     using Cfg = GruF2Cfg<KX>;
+    // debug timeline (CF_TC_TRACE): block 0 records (tag, SM clock) pairs for steps 36..39 of each role
+    int tr_n = 0;
+#define CF_TR(region, step, tag)                                                                   \
+    do {                                                                                           \
+        if (trace && blockIdx.x == 0 && (step) >= 36 && (step) < 40 && tr_n < 200) {               \
+            long long gt_;                                                                         \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                \
+            trace[((region) * 200 + tr_n) * 2] = (tag) + 1000 * (gt_ % 100000000LL);               \
+            trace[((region) * 200 + tr_n) * 2 + 1] = clock64();                                    \
+            ++tr_n;                                                                                \
+        }                                                                                          \
+    } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][16], then w_bar
     uint64_t* w_bar = &bars[32];
@@ -1414,48 +1428,47 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 18) {
-        // ------------------------------------------------------------ producer (both rings, polling)
+    if (warp >= 18) {
+        // ------------------------------------------------------------ producer of chain (warp - 18)
         if (lane == 0) {
-            mbar_expect_tx(w_bar, Cfg::kWBytes);
-            const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
-            for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
-                const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
-                bulk_g2s(smem + off, wsrc + off, n, w_bar);
+            const int c = warp - 18;
+            if (c == 0) {
+                mbar_expect_tx(w_bar, Cfg::kWBytes);
+                const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
+                for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
+                    const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
+                    bulk_g2s(smem + off, wsrc + off, n, w_bar);
+                }
             }
             constexpr size_t plane = (size_t)128 * KX * 2;
-            constexpr int kAhead = 2;
+            constexpr int kAhead = 3;                 // blocks pulled into L2 ahead of the ring
             const uint8_t* xbase = reinterpret_cast<const uint8_t*>(x_blocks);
-            int total[2] = {tiles_of(0) * kWindow, tiles_of(1) * kWindow};
-            int gs[2] = {0, 0}, kk[2] = {0, 0};
-            uint32_t cn[2] = {0, 0};
-            for (int c = 0; c < 2; ++c)
-                for (int a = 0; a < kAhead && a < total[c]; ++a) bulk_prefetch_l2(xbase + blk_of(c, a) * 2 * plane, 2 * plane);
-            while (gs[0] < total[0] || gs[1] < total[1]) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (gs[c] >= total[c]) continue;
-                    uint64_t* b = &bars[16 * c];
-                    const int st = cn[c] % Cfg::kStages;
-                    if (!mbar_test_wait(&b[Cfg::kBarEmpty + st], ((cn[c] / Cfg::kStages) & 1) ^ 1)) continue;
-                    const uint8_t* xb = xbase + blk_of(c, gs[c]) * 2 * plane;
-                    if (kk[c] == 0 && gs[c] + kAhead < total[c])
-                        bulk_prefetch_l2(xbase + blk_of(c, gs[c] + kAhead) * 2 * plane, 2 * plane);
+            const int total = tiles_of(c) * kWindow;
+            uint64_t* b = &bars[16 * c];
+            for (int a = 0; a < kAhead && a < total; ++a) bulk_prefetch_l2(xbase + blk_of(c, a) * 2 * plane, 2 * plane);
+            uint32_t cn = 0;
+            for (int gs = 0; gs < total; ++gs) {
+                const uint8_t* xb = xbase + blk_of(c, gs) * 2 * plane;
+                if (gs + kAhead < total) bulk_prefetch_l2(xbase + blk_of(c, gs + kAhead) * 2 * plane, 2 * plane);
+                for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
+                    const int st = cn % Cfg::kStages;
+                    mbar_wait(&b[Cfg::kBarEmpty + st], ((cn / Cfg::kStages) & 1) ^ 1);
                     uint8_t* dst = smem + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
                     mbar_expect_tx(&b[Cfg::kBarFull + st], 8192);
-                    bulk_g2s(dst, xb + kk[c] * 4096, 4096, &b[Cfg::kBarFull + st]);
-                    bulk_g2s(dst + 4096, xb + plane + kk[c] * 4096, 4096, &b[Cfg::kBarFull + st]);
-                    ++cn[c];
-                    if (++kk[c] == Cfg::kChunks) { kk[c] = 0; ++gs[c]; }
+                    bulk_g2s(dst, xb + kk * 4096, 4096, &b[Cfg::kBarFull + st]);
+                    bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, &b[Cfg::kBarFull + st]);
                 }
             }
         }
     } else if (warp >= 16) {
         // ------------------------------------------------------------ MMA issuer of chain (warp - 16)
-        if (lane == 0) {
+        // Warp-converged: all lanes run the control flow and the waits, one elected lane issues
+        // (descriptor arithmetic stays on the uniform datapath: ~10 instead of ~80 cycles per MMA).
+        {
             constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
             constexpr uint32_t idesc_c = make_idesc_bf16(128, kH);
             constexpr uint32_t idesc_x = make_idesc_bf16(128, kNX);
+            const uint32_t elected = elect_one();
             const int c = warp - 16;
             const uint32_t s0 = smem_u32(smem);
             uint64_t* b = &bars[16 * c];
@@ -1467,15 +1480,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 const uint32_t par = gs & 1;
                 // x part: needs the previous step's accumulators drained
                 if (gs > 0) mbar_wait(&b[Cfg::kBarCfree], (gs - 1) & 1);
+                if (lane == 0) CF_TR(c, gs, 10);
                 for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
                     const int st = cn % Cfg::kStages;
-                    // keep the in-order tensor queue shallow (at most kXDepth x chunks of this chain in flight)
-                    // so that the other chain's state-part MMAs, which sit on its critical path, do not
-                    // wait behind a long run of x chunks: chunk cn - kXDepth must have completed
-                    if (cn >= (uint32_t)kXDepth) {
-                        const uint32_t pc = cn - kXDepth;
-                        mbar_wait(&b[Cfg::kBarEmpty + pc % Cfg::kStages], (pc / Cfg::kStages) & 1);
-                    }
                     mbar_wait(&b[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
                     tc_fence_after_sync();
                     const uint32_t a0 = s0 + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
@@ -1483,12 +1490,14 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
                         const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
-                        umma_bf16(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0);
+                        umma_bf16_pred(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0, elected);
                     }
-                    umma_commit(&b[Cfg::kBarEmpty + st]);
+                    umma_commit_pred(&b[Cfg::kBarEmpty + st], elected);
+                    if (lane == 0) CF_TR(c, gs, 20 + kk);
                 }
                 // state part of the gates
                 mbar_wait(&b[Cfg::kBarH], par);
+                if (lane == 0) CF_TR(c, gs, 30);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -1496,11 +1505,13 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
 #pragma unroll
                     for (int kk = 0; kk < kH / 16; ++kk)
-                        umma_bf16_ts(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1);
+                        umma_bf16_ts_pred(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1, elected);
                 }
-                umma_commit(&b[Cfg::kBarG]);
+                umma_commit_pred(&b[Cfg::kBarG], elected);
+                if (lane == 0) CF_TR(c, gs, 31);
                 // state part of the candidate
                 mbar_wait(&b[Cfg::kBarRh], par);
+                if (lane == 0) CF_TR(c, gs, 40);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -1508,9 +1519,10 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
 #pragma unroll
                     for (int kk = 0; kk < kH / 16; ++kk)
-                        umma_bf16_ts(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1);
+                        umma_bf16_ts_pred(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1, elected);
                 }
-                umma_commit(&b[Cfg::kBarC]);
+                umma_commit_pred(&b[Cfg::kBarC], elected);
+                if (lane == 0) CF_TR(c, gs, 41);
             }
         }
     } else {
@@ -1546,6 +1558,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 const size_t blk = blk_of(chain, gs);
                 // ---- reset gate -> r*h operand
                 mbar_wait(&b[Cfg::kBarG], par);
+                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 50);
                 tc_fence_after_sync();
                 {
                     uint32_t ar[32];
@@ -1573,6 +1586,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b[Cfg::kBarRh]);
+                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 51);
                 // ---- update gate while the candidate MMA runs
                 {
                     uint32_t au[32];
@@ -1589,7 +1603,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     }
                 }
                 // ---- candidate, new state h = c + u (h - c)
+                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 52);
                 mbar_wait(&b[Cfg::kBarC], par);
+                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 53);
                 tc_fence_after_sync();
                 uint32_t ac[32];
                 tmem_ld16_nowait(t_acc + 2 * kH, ac);
@@ -1598,6 +1614,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b[Cfg::kBarCfree]);      // accumulators drained: next x part may start
+                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 54);
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -1621,6 +1638,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
                 }
+                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 55);
                 if (y_out) {
                     // next layer's A operand: block {hi, lo} x [16][128][8], features dir*64 + j
                     __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 8;
@@ -1643,6 +1661,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
     __syncthreads();
     if (warp == 16) tmem_dealloc<512>(tmem);
 }
+
+#undef CF_TR
 
 // ====================================================================== TK5: head
 // p = sigmoid(part_fw + part_bw + b), scattered to sample order with the padding cut (infer.py:47).
@@ -1797,14 +1817,35 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 }
                 ProfScope ps(prof, KC_K4_GRU, stream);
                 if (e->fused_variant == 2) {
+                    long long* trace_dev = nullptr;
+                    if (getenv("CF_TC_TRACE") && !e->trace_done && L.in != kC) {
+                        CF_CUDA(cudaMalloc(&trace_dev, 5 * 200 * 2 * sizeof(long long)));
+                        CF_CUDA(cudaMemsetAsync(trace_dev, 0, 5 * 200 * 2 * sizeof(long long), stream));
+                    }
                     const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
                     if (L.in == kC)
-                        tc_gru_fused2_kernel<32><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth);
+                        tc_gru_fused2_kernel<32><<<grid2, 640, GruF2Cfg<32>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth, nullptr);
                     else
-                        tc_gru_fused2_kernel<128><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth);
+                        tc_gru_fused2_kernel<128><<<grid2, 640, GruF2Cfg<128>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth,
+                            trace_dev);
                     CF_LAUNCHED();
+                    if (trace_dev) {
+                        // debug: dump the timeline of block 0 and stop tracing
+                        CF_CUDA(cudaStreamSynchronize(stream));
+                        std::vector<long long> host(5 * 200 * 2);
+                        CF_CUDA(cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                        if (FILE* f = fopen(getenv("CF_TC_TRACE"), "w")) {
+                            for (int rg = 0; rg < 5; ++rg)
+                                for (int k = 0; k < 200; ++k)
+                                    if (host[(rg * 200 + k) * 2 + 1])
+                                        fprintf(f, "%d %lld %lld\n", rg, host[(rg * 200 + k) * 2], host[(rg * 200 + k) * 2 + 1]);
+                            fclose(f);
+                        }
+                        cudaFree(trace_dev);
+                        e->trace_done = true;
+                    }
                     a_in = yo;
                     head_parts = 4;
                     continue;
