@@ -1,6 +1,7 @@
 // C-ABI entry points (include/catfish_b200.h): model construction, ragged-batch planning and
 // the kernel sequence of one inference call.  No CPU fallback: every entry that computes
 // requires a CUDA device and fails with CF_ERR_NO_DEVICE / CF_ERR_CUDA otherwise.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -244,7 +245,7 @@ struct cf_model {
     cf::HostBuf pin_plan;            // offsets + win_off staging
     cudaEvent_t plan_copied = nullptr;
     cf::DevBuf plan_dev;             // offsets[R+1] | win_off[R+1]
-    cf::DevBuf stats, wide_flags, wide_scratch;
+    cf::DevBuf stats, wide_flags, wide_scratch, k1_chunked, k1_chunk_tab;
     cf::DevBuf tab_src, tab_valid, tab_read;
     cf::DevBuf probs_internal;
     cf::IntervalScratch k6;
@@ -330,6 +331,46 @@ static int upload_plan(cf_model* m, const int64_t* offsets, const BatchPlan& p, 
     return CF_OK;
 }
 
+// Median / MAD of every read: one CTA per read, or several CTAs per read when reads are long or few.
+struct StatsScratch {
+    DevBuf* flags; DevBuf* wide; DevBuf* chunked; DevBuf* chunk_tab;
+};
+static bool stats_use_chunks(const int64_t* offsets, int32_t n_reads) {
+    const int64_t total = offsets[n_reads] - offsets[0];
+    return n_reads <= 8192 && (total / n_reads >= 2 * kK1ChunkSamples || n_reads < 2 * 148);
+}
+static int compute_read_stats(const int16_t* raw0, const int64_t* offsets_host, const int64_t* offsets_dev,
+                              int32_t n_reads, double* stats, StatsScratch sc, cudaStream_t stream) {
+    CF_TRY(sc.flags->ensure(sizeof(int32_t) * (size_t)n_reads));
+    CF_TRY(sc.wide->ensure(k1_wide_scratch_bytes(kWideSlots)));
+    if (!stats_use_chunks(offsets_host, n_reads))
+        return k1_read_stats(raw0, offsets_dev, n_reads, stats, sc.flags->as<int32_t>(), sc.wide->as<uint32_t>(), kWideSlots, stream);
+    // chunk table: [beg int64 | read int32 | len int32] per chunk, built on the host
+    std::vector<int64_t> beg;
+    std::vector<int32_t> rd, ln;
+    for (int32_t r = 0; r < n_reads; ++r) {
+        const int64_t b0 = offsets_host[r] - offsets_host[0], len = offsets_host[r + 1] - offsets_host[r];
+        for (int64_t o = 0; o < len; o += kK1ChunkSamples) {
+            beg.push_back(b0 + o);
+            rd.push_back(r);
+            ln.push_back((int32_t)std::min<int64_t>(kK1ChunkSamples, len - o));
+        }
+    }
+    const size_t nc = beg.size();
+    CF_TRY(sc.chunk_tab->ensure(nc * 16 + 64));
+    CF_TRY(sc.chunked->ensure(k1_chunked_scratch_bytes(n_reads)));
+    uint8_t* tab = static_cast<uint8_t*>(sc.chunk_tab->ptr);
+    if (nc) {
+        CF_CUDA(cudaMemcpyAsync(tab, beg.data(), nc * 8, cudaMemcpyHostToDevice, stream));
+        CF_CUDA(cudaMemcpyAsync(tab + nc * 8, rd.data(), nc * 4, cudaMemcpyHostToDevice, stream));
+        CF_CUDA(cudaMemcpyAsync(tab + nc * 12, ln.data(), nc * 4, cudaMemcpyHostToDevice, stream));
+        CF_CUDA(cudaStreamSynchronize(stream));            // the host vectors are pageable and local
+    }
+    return k1_read_stats_chunked(raw0, offsets_dev, n_reads, reinterpret_cast<int32_t*>(tab + nc * 8),
+                                 reinterpret_cast<int64_t*>(tab), reinterpret_cast<int32_t*>(tab + nc * 12), (int64_t)nc,
+                                 sc.chunked->ptr, stats, sc.flags->as<int32_t>(), sc.wide->as<uint32_t>(), kWideSlots, stream);
+}
+
 static int ensure_table(cf_model* m, int64_t n_tiles, WindowTable* tab) {
     const size_t slots = (size_t)n_tiles * kTileWindows;
     CF_TRY(m->tab_src.ensure(slots * sizeof(int64_t)));
@@ -356,8 +397,6 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
     const int64_t *offsets_dev, *win_off_dev;
     CF_TRY(upload_plan(m, offsets_host, plan, stream, &offsets_dev, &win_off_dev));
     CF_TRY(m->stats.ensure(sizeof(double) * 2 * (size_t)n_reads));
-    CF_TRY(m->wide_flags.ensure(sizeof(int32_t) * (size_t)n_reads));
-    CF_TRY(m->wide_scratch.ensure(k1_wide_scratch_bytes(kWideSlots)));
     WindowTable tab;
     CF_TRY(ensure_table(m, plan.n_tiles, &tab));
     float* probs = probs_dev;
@@ -366,9 +405,13 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
         probs = m->probs_internal.as<float>();
     }
     {
-        ProfScope ps(&m->prof, KC_K1_STATS, stream, 2);
-        CF_TRY(k1_read_stats(raw0, offsets_dev, n_reads, m->stats.as<double>(), m->wide_flags.as<int32_t>(),
-                             m->wide_scratch.as<uint32_t>(), kWideSlots, stream));
+        StatsScratch sc{&m->wide_flags, &m->wide_scratch, &m->k1_chunked, &m->k1_chunk_tab};
+        const bool chunks = stats_use_chunks(offsets_host, n_reads);
+        if (chunks) {   // allocate before the timed bracket
+            CF_TRY(m->k1_chunked.ensure(k1_chunked_scratch_bytes(n_reads)));
+        }
+        ProfScope ps(&m->prof, KC_K1_STATS, stream, chunks ? 5 : 2);
+        CF_TRY(compute_read_stats(raw0, offsets_host, offsets_dev, n_reads, m->stats.as<double>(), sc, stream));
     }
     {
         ProfScope ps(&m->prof, KC_K1_TABLE, stream);
@@ -519,7 +562,7 @@ void cf_model_destroy(cf_model* m) {
     cf::simt_destroy(m->simt);
     cf::tc_destroy(m->tc);
     m->pin_plan.release(); m->plan_dev.release(); m->stats.release(); m->wide_flags.release();
-    m->wide_scratch.release(); m->tab_src.release(); m->tab_valid.release(); m->tab_read.release();
+    m->wide_scratch.release(); m->k1_chunked.release(); m->k1_chunk_tab.release(); m->tab_src.release(); m->tab_valid.release(); m->tab_read.release();
     m->probs_internal.release();
     m->k6.bits.release(); m->k6.block_cnt.release(); m->k6.read_cnt.release(); m->k6.misc.release();
     m->h_raw.release(); m->h_intervals.release(); m->h_ioff.release(); m->h_probs.release();
@@ -563,6 +606,7 @@ int cf_model_reserve(cf_model* m, int64_t max_samples, int32_t max_reads) {
     CF_TRY(m->stats.ensure(sizeof(double) * 2 * (size_t)max_reads));
     CF_TRY(m->wide_flags.ensure(sizeof(int32_t) * (size_t)max_reads));
     CF_TRY(m->wide_scratch.ensure(cf::k1_wide_scratch_bytes(cf::kWideSlots)));
+    if (max_reads > 0 && max_reads <= 8192) CF_TRY(m->k1_chunked.ensure(cf::k1_chunked_scratch_bytes(max_reads)));
     CF_TRY(m->probs_internal.ensure(sizeof(float) * (size_t)max_samples));
     return CF_OK;
 }
@@ -675,17 +719,17 @@ int cf_normalize_reads(int32_t device, const int16_t* raw_dev, const int64_t* of
     CF_TRY(upload_offsets(offsets_host, n_reads, off, st));
     cf::DevBuf* flags = tmp.make();
     cf::DevBuf* wide = tmp.make();
+    cf::DevBuf* chunked = tmp.make();
+    cf::DevBuf* chunk_tab = tmp.make();
     cf::DevBuf* stats_tmp = tmp.make();
-    CF_TRY(flags->ensure(sizeof(int32_t) * (size_t)n_reads));
-    CF_TRY(wide->ensure(cf::k1_wide_scratch_bytes(cf::kWideSlots)));
     double* stats = stats_dev;
     if (!stats) {
         CF_TRY(stats_tmp->ensure(sizeof(double) * 2 * (size_t)n_reads));
         stats = stats_tmp->as<double>();
     }
     const int16_t* raw0 = raw_dev + offsets_host[0];
-    CF_TRY(cf::k1_read_stats(raw0, off->as<int64_t>(), n_reads, stats, flags->as<int32_t>(),
-                             wide->as<uint32_t>(), cf::kWideSlots, st));
+    cf::StatsScratch sc{flags, wide, chunked, chunk_tab};
+    CF_TRY(cf::compute_read_stats(raw0, offsets_host, off->as<int64_t>(), n_reads, stats, sc, st));
     if (norm_dev)
         CF_TRY(cf::k1_normalize_f64(raw0, off->as<int64_t>(), n_reads, offsets_host[n_reads] - offsets_host[0],
                                     stats, norm_dev, st));

@@ -139,6 +139,12 @@ int k1_normalize_f64(const int16_t* raw, const int64_t* offsets_dev, int32_t n_r
 int k1_window_table(const int64_t* offsets_dev, const int64_t* win_off_dev, int32_t n_reads,
                     int64_t total_windows, int64_t n_tiles, WindowTable tab, cudaStream_t stream);
 size_t k1_wide_scratch_bytes(int n_slots);
+constexpr int kK1ChunkSamples = 32768;
+size_t k1_chunked_scratch_bytes(int n_reads);
+int k1_read_stats_chunked(const int16_t* raw, const int64_t* offsets_dev, int32_t n_reads, const int32_t* chunk_read,
+                          const int64_t* chunk_beg, const int32_t* chunk_len, int64_t n_chunks, void* scratch,
+                          double* stats, int32_t* wide_flags, uint32_t* wide_scratch, int n_wide_slots,
+                          cudaStream_t stream);
 
 // ---------------------------------------------------------------- k6: interval calling
 struct IntervalScratch {

@@ -198,6 +198,116 @@ int k1_read_stats(const int16_t* raw, const int64_t* offsets_dev, int32_t n_read
     return CF_OK;
 }
 
+// ---------------------------------------------------------------- long reads: several CTAs per read
+// A read is cut into chunks of kChunkSamples; every chunk is one CTA.  Pass 1 reduces the value
+// range per read (atomicMin/Max), pass 2 builds a shared-memory histogram of the chunk relative to
+// the read's minimum and adds its non-empty bins to the read's global histogram, pass 3 (one CTA per
+// read) evaluates the order statistics exactly as the one-CTA kernel does.  Used when reads are long
+// or few, so that one 1M-sample read does not sit on a single SM.
+__global__ void __launch_bounds__(kStatsThreads)
+k1_minmax_chunks_kernel(const int16_t* __restrict__ raw, const int32_t* __restrict__ chunk_read,
+                        const int64_t* __restrict__ chunk_beg, const int32_t* __restrict__ chunk_len,
+                        int* __restrict__ gmin, int* __restrict__ gmax) {
+    __shared__ int red_min[kStatsThreads / 32], red_max[kStatsThreads / 32];
+    const int c = blockIdx.x;
+    int vmin = 32767, vmax = -32768;
+    for_each_i16(raw + chunk_beg[c], chunk_len[c], [&](int v) { vmin = min(vmin, v); vmax = max(vmax, v); });
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    }
+    if ((threadIdx.x & 31) == 0) { red_min[threadIdx.x >> 5] = vmin; red_max[threadIdx.x >> 5] = vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < kStatsThreads / 32; ++w) { vmin = min(vmin, red_min[w]); vmax = max(vmax, red_max[w]); }
+        const int r = chunk_read[c];
+        atomicMin(&gmin[r], vmin);
+        atomicMax(&gmax[r], vmax);
+    }
+}
+
+__global__ void __launch_bounds__(kStatsThreads)
+k1_hist_chunks_kernel(const int16_t* __restrict__ raw, const int32_t* __restrict__ chunk_read,
+                      const int64_t* __restrict__ chunk_beg, const int32_t* __restrict__ chunk_len,
+                      const int* __restrict__ gmin, const int* __restrict__ gmax, unsigned* __restrict__ ghist) {
+    __shared__ unsigned hist[kSmemBins];
+    const int c = blockIdx.x;
+    const int r = chunk_read[c];
+    const int base = gmin[r];
+    const int nb = gmax[r] - base + 1;
+    if (nb > kSmemBins) return;                 // wide read: handled by k1_stats_wide_kernel
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for_each_i16(raw + chunk_beg[c], chunk_len[c], [&](int v) { atomicAdd(&hist[v - base], 1u); });
+    __syncthreads();
+    unsigned* gh = ghist + (size_t)r * kSmemBins;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const unsigned v = hist[i];
+        if (v) atomicAdd(&gh[i], v);
+    }
+}
+
+__global__ void __launch_bounds__(kStatsThreads)
+k1_stats_from_ghist_kernel(const int64_t* __restrict__ offsets, const int* __restrict__ gmin,
+                           const int* __restrict__ gmax, const unsigned* __restrict__ ghist,
+                           double* __restrict__ stats, int32_t* __restrict__ wide_flags) {
+    __shared__ unsigned hist[kSmemBins];
+    __shared__ unsigned warp_sums[kStatsThreads / 32];
+    __shared__ int sel[4];
+    const int r = blockIdx.x;
+    const int64_t n = offsets[r + 1] - offsets[r];
+    if (threadIdx.x == 0) wide_flags[r] = 0;
+    if (n <= 0) {
+        if (threadIdx.x == 0) { stats[2 * r] = nan(""); stats[2 * r + 1] = nan(""); }
+        return;
+    }
+    const int base = gmin[r];
+    const int nb = gmax[r] - base + 1;
+    if (nb > kSmemBins) {
+        if (threadIdx.x == 0) wide_flags[r] = 1;
+        return;
+    }
+    const unsigned* gh = ghist + (size_t)r * kSmemBins;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = gh[i];
+    __syncthreads();
+    stats_from_hist(hist, base, nb, (unsigned)n, stats + 2 * r, sel, warp_sums);
+}
+
+__global__ void k1_init_minmax_kernel(int* __restrict__ gmin, int* __restrict__ gmax, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { gmin[i] = 32767; gmax[i] = -32768; }
+}
+
+size_t k1_chunked_scratch_bytes(int n_reads) {
+    return (size_t)n_reads * (kSmemBins * sizeof(unsigned) + 2 * sizeof(int)) + 256;
+}
+
+int k1_read_stats_chunked(const int16_t* raw, const int64_t* offsets_dev, int32_t n_reads, const int32_t* chunk_read,
+                          const int64_t* chunk_beg, const int32_t* chunk_len, int64_t n_chunks, void* scratch,
+                          double* stats, int32_t* wide_flags, uint32_t* wide_scratch, int n_wide_slots,
+                          cudaStream_t stream) {
+    if (n_reads <= 0) return CF_OK;
+    unsigned* ghist = static_cast<unsigned*>(scratch);
+    int* gmin = reinterpret_cast<int*>(ghist + (size_t)n_reads * kSmemBins);
+    int* gmax = gmin + n_reads;
+    CF_CUDA(cudaMemsetAsync(ghist, 0, (size_t)n_reads * kSmemBins * sizeof(unsigned), stream));
+    k1_init_minmax_kernel<<<(unsigned)ceil_div(n_reads, 256), 256, 0, stream>>>(gmin, gmax, n_reads);
+    CF_LAUNCHED();
+    if (n_chunks > 0) {
+        k1_minmax_chunks_kernel<<<(unsigned)n_chunks, kStatsThreads, 0, stream>>>(raw, chunk_read, chunk_beg, chunk_len, gmin, gmax);
+        CF_LAUNCHED();
+        k1_hist_chunks_kernel<<<(unsigned)n_chunks, kStatsThreads, 0, stream>>>(raw, chunk_read, chunk_beg, chunk_len, gmin, gmax, ghist);
+        CF_LAUNCHED();
+    }
+    k1_stats_from_ghist_kernel<<<n_reads, kStatsThreads, 0, stream>>>(offsets_dev, gmin, gmax, ghist, stats, wide_flags);
+    CF_LAUNCHED();
+    const int slots = n_reads < n_wide_slots ? n_reads : n_wide_slots;
+    k1_stats_wide_kernel<<<slots, kStatsThreads, 0, stream>>>(raw, offsets_dev, n_reads, stats, wide_flags, wide_scratch);
+    CF_LAUNCHED();
+    return CF_OK;
+}
+
 // ---------------------------------------------------------------- (raw - shift) / scale in fp64
 __device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t i) {
     int lo = 0, hi = n;                   // largest s with off[s] <= i, off has n+1 entries

@@ -171,3 +171,15 @@ def test_properties_at_scale():
         labels = postprocess.correct_short(postprocess.class_from_threshold(s.astype(np.float64)))
         assert h == postprocess.hp_in_pred(labels)
         assert np.all((s >= 0) & (s <= 1))
+
+
+def test_ultra_long_read_vs_oracle(shipped_weights):
+    """BASELINE configs[4]: a 1M-sample read (28 572 windows) end to end against the CPU oracle."""
+    m = _model("ResNetRNN", "auto")
+    raw = synth.synth_read(1_000_000, 4242)
+    hps, lengths, scores = infer.infer_reads([raw], m, return_scores=True)
+    graph = tf_graph.TorchGraph(shipped_weights)
+    want_hps, want_len, want_scores = postprocess.infer_read(raw, graph.infer)
+    assert lengths[0] == want_len == 1_000_000
+    assert np.abs(scores[0] - want_scores).max() < PROB_TOL
+    _check_intervals(hps[0], scores[0], want_scores)

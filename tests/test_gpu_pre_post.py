@@ -35,6 +35,17 @@ def test_read_stats_ragged_batch_exact():
         assert shift == want_shift and scale == want_scale, (len(r), shift, want_shift, scale, want_scale)
 
 
+def test_read_stats_many_short_reads_one_cta_per_read():
+    """>= 296 short reads take the one-CTA-per-read kernel (fewer, longer reads are chunked over CTAs)."""
+    rng = np.random.default_rng(2)
+    reads = synth.synth_reads(rng.integers(1, 3000, size=400), base_seed=2000)
+    reads[7] = rng.integers(-32768, 32768, size=999).astype(np.int16)        # wide path inside the batch
+    st = infer.read_stats(reads)
+    for r, (shift, scale) in zip(reads, st):
+        want_shift = np.median(r)
+        assert shift == want_shift and scale == np.median(np.abs(r - want_shift))
+
+
 def test_read_stats_long_read():
     raw = synth.synth_read(1_000_000, 77)
     st = infer.read_stats([raw])[0]
