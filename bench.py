@@ -305,6 +305,13 @@ def run_b200(args):
             achieved = BYTES_PER_SAMPLE.get(name, 0.0) * units_per_launch / per_launch_s / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm"], "traffic": None}
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if name in tj:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
+                roof["traffic"] = tj[name]["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/r1_traffic.json (%s)" % tj.get("source", "ncu")
         roof.update({"kernel": name, "launches": dom_launches, "avg_launch_ms": dom_ms / max(1, dom_launches),
                      "share_of_step": dom_ms / ms_dev, "peak_source": peaks["source"] + " (sustained)",
                      "algorithmic_per_sample": FLOPS_PER_SAMPLE.get(name, BYTES_PER_SAMPLE.get(name))})

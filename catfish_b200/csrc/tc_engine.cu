@@ -90,7 +90,7 @@ struct TcEngine {
     int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
     int conv_variant = 2;             // 2 = one round per position (tc_conv2_kernel); 1 = three rounds (CF_TC_CONV=1)
     bool trace_done = false;
-    int x_depth = 2;                  // x chunks of one chain allowed in the tensor queue (CF_TC_XDEPTH)
+    int x_depth = 0;                  // x blocks prefetched into L2 ahead of the ring (CF_TC_XDEPTH); measured: no gain, extra DRAM reads
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
 };
@@ -121,7 +121,7 @@ TcEngine* tc_create(const HostModel& hm) {
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
     if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
     if (const char* env = getenv("CF_TC_CONV")) e->conv_variant = atoi(env) == 1 ? 1 : 2;
-    if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(1, atoi(env));
+    if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(0, atoi(env));
     if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
@@ -1441,7 +1441,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 }
             }
             constexpr size_t plane = (size_t)128 * KX * 2;
-            constexpr int kAhead = 3;                 // blocks pulled into L2 ahead of the ring
+            const int kAhead = kXDepth;               // blocks pulled into L2 ahead of the ring (0 = no prefetch)
             const uint8_t* xbase = reinterpret_cast<const uint8_t*>(x_blocks);
             const int total = tiles_of(c) * kWindow;
             uint64_t* b = &bars[16 * c];

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Per-launch DRAM traffic of the main kernels from an `ncu --set full` report -> profiles/r1_traffic.json.
+
+    python tools/extract_traffic.py gpurun_out/r1_prof_main.ncu-rep
+
+bench.py reads the JSON to fill roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch,
+averaged over the captured launches of a kernel class).
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+CLASSES = {"tc_gru_fused2_kernel": "k4_gru_recurrence", "tc_gru_fused_kernel": "k4_gru_recurrence",
+           "tc_conv2_kernel": "k2_conv_stack", "tc_conv_kernel": "k2_conv_stack"}
+UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+if __name__ == "__main__":
+    rep = sys.argv[1]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    acc = {}
+    for r in rows[2:]:
+        name = r[ik]
+        cls = next((v for k, v in CLASSES.items() if k in name), None)
+        if cls is None:
+            continue
+        b = float(r[ir]) * UNITS[units[ir]] + float(r[iw]) * UNITS[units[iw]]
+        acc.setdefault(cls, []).append(b)
+    res = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v)} for k, v in acc.items()}
+    res["source"] = os.path.basename(rep)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "r1_traffic.json")
+    with open(path, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res))
