@@ -244,6 +244,8 @@ struct cf_model {
     // per-batch scratch
     cf::HostBuf pin_plan;            // offsets + win_off staging
     cudaEvent_t plan_copied = nullptr;
+    cf::HostBuf pin_chunks;          // K1 chunk-table staging
+    cudaEvent_t chunks_copied = nullptr;
     cf::DevBuf plan_dev;             // offsets[R+1] | win_off[R+1]
     cf::DevBuf stats, wide_flags, wide_scratch, k1_chunked, k1_chunk_tab;
     cf::DevBuf tab_src, tab_valid, tab_read;
@@ -334,6 +336,8 @@ static int upload_plan(cf_model* m, const int64_t* offsets, const BatchPlan& p, 
 // Median / MAD of every read: one CTA per read, or several CTAs per read when reads are long or few.
 struct StatsScratch {
     DevBuf* flags; DevBuf* wide; DevBuf* chunked; DevBuf* chunk_tab;
+    HostBuf* pinned = nullptr;        // optional pinned staging for the chunk table (keeps the call asynchronous)
+    cudaEvent_t* staged = nullptr;    // recorded after the staging copy; waited on before the buffer is reused
 };
 static bool stats_use_chunks(const int64_t* offsets, int32_t n_reads) {
     const int64_t total = offsets[n_reads] - offsets[0];
@@ -346,25 +350,41 @@ static int compute_read_stats(const int16_t* raw0, const int64_t* offsets_host, 
     if (!stats_use_chunks(offsets_host, n_reads))
         return k1_read_stats(raw0, offsets_dev, n_reads, stats, sc.flags->as<int32_t>(), sc.wide->as<uint32_t>(), kWideSlots, stream);
     // chunk table: [beg int64 | read int32 | len int32] per chunk, built on the host
-    std::vector<int64_t> beg;
-    std::vector<int32_t> rd, ln;
+    size_t nc = 0;
+    for (int32_t r = 0; r < n_reads; ++r) nc += (size_t)ceil_div(offsets_host[r + 1] - offsets_host[r], kK1ChunkSamples);
+    std::vector<uint8_t> pageable;
+    uint8_t* host = nullptr;
+    if (sc.pinned) {
+        if (*sc.staged) CF_CUDA(cudaEventSynchronize(*sc.staged));
+        CF_TRY(sc.pinned->ensure(nc * 16 + 64));
+        host = sc.pinned->as<uint8_t>();
+    } else {
+        pageable.resize(nc * 16 + 64);
+        host = pageable.data();
+    }
+    int64_t* beg = reinterpret_cast<int64_t*>(host);
+    int32_t* rd = reinterpret_cast<int32_t*>(host + nc * 8);
+    int32_t* ln = reinterpret_cast<int32_t*>(host + nc * 12);
+    size_t k = 0;
     for (int32_t r = 0; r < n_reads; ++r) {
         const int64_t b0 = offsets_host[r] - offsets_host[0], len = offsets_host[r + 1] - offsets_host[r];
-        for (int64_t o = 0; o < len; o += kK1ChunkSamples) {
-            beg.push_back(b0 + o);
-            rd.push_back(r);
-            ln.push_back((int32_t)std::min<int64_t>(kK1ChunkSamples, len - o));
+        for (int64_t o = 0; o < len; o += kK1ChunkSamples, ++k) {
+            beg[k] = b0 + o;
+            rd[k] = r;
+            ln[k] = (int32_t)std::min<int64_t>(kK1ChunkSamples, len - o);
         }
     }
-    const size_t nc = beg.size();
     CF_TRY(sc.chunk_tab->ensure(nc * 16 + 64));
     CF_TRY(sc.chunked->ensure(k1_chunked_scratch_bytes(n_reads)));
     uint8_t* tab = static_cast<uint8_t*>(sc.chunk_tab->ptr);
     if (nc) {
-        CF_CUDA(cudaMemcpyAsync(tab, beg.data(), nc * 8, cudaMemcpyHostToDevice, stream));
-        CF_CUDA(cudaMemcpyAsync(tab + nc * 8, rd.data(), nc * 4, cudaMemcpyHostToDevice, stream));
-        CF_CUDA(cudaMemcpyAsync(tab + nc * 12, ln.data(), nc * 4, cudaMemcpyHostToDevice, stream));
-        CF_CUDA(cudaStreamSynchronize(stream));            // the host vectors are pageable and local
+        CF_CUDA(cudaMemcpyAsync(tab, host, nc * 16, cudaMemcpyHostToDevice, stream));
+        if (sc.pinned) {
+            if (!*sc.staged) CF_CUDA(cudaEventCreateWithFlags(sc.staged, cudaEventDisableTiming));
+            CF_CUDA(cudaEventRecord(*sc.staged, stream));
+        } else {
+            CF_CUDA(cudaStreamSynchronize(stream));        // pageable, local staging
+        }
     }
     return k1_read_stats_chunked(raw0, offsets_dev, n_reads, reinterpret_cast<int32_t*>(tab + nc * 8),
                                  reinterpret_cast<int64_t*>(tab), reinterpret_cast<int32_t*>(tab + nc * 12), (int64_t)nc,
@@ -405,7 +425,7 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
         probs = m->probs_internal.as<float>();
     }
     {
-        StatsScratch sc{&m->wide_flags, &m->wide_scratch, &m->k1_chunked, &m->k1_chunk_tab};
+        StatsScratch sc{&m->wide_flags, &m->wide_scratch, &m->k1_chunked, &m->k1_chunk_tab, &m->pin_chunks, &m->chunks_copied};
         const bool chunks = stats_use_chunks(offsets_host, n_reads);
         if (chunks) {   // allocate before the timed bracket
             CF_TRY(m->k1_chunked.ensure(k1_chunked_scratch_bytes(n_reads)));
@@ -569,6 +589,8 @@ void cf_model_destroy(cf_model* m) {
     m->pin_io.release();
     m->prof.release();
     if (m->plan_copied) cudaEventDestroy(m->plan_copied);
+    m->pin_chunks.release();
+    if (m->chunks_copied) cudaEventDestroy(m->chunks_copied);
     delete m;
 }
 

@@ -1354,7 +1354,7 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
 // A lo 224..255.  Shared memory: weights (147 KB) + one 5-stage x ring per chain (80 KB).
 //   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
 //   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
-//   warp 18 / 19     : producer of chain 0 / 1 (weights once, then the chain's x ring)
+//   warp 18          : lanes 0 / 1 = producer of chain 0 / 1 (weights once, then the chain's x ring)
 template <int KX> struct GruF2Cfg {
     static constexpr int kChunks = KX / 16;
     static constexpr int kStages = 5;
@@ -1371,7 +1371,7 @@ template <int KX> struct GruF2Cfg {
 };
 
 template <int KX>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(608, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
                      const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth,
@@ -1421,17 +1421,22 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         mbar_init(w_bar, 1);
         fence_mbar_init();
     }
+#ifndef CF_PRECISE_ACT
+    // bias pre-multiplied by the activation's argument scale, so that bias add + scaling is one FFMA
+    if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x] * (threadIdx.x < 2 * kH ? kSigArgScale : kTanhArgScale);
+#else
     if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x];
+#endif
     if (warp == 16) tmem_alloc<512>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= 18) {
-        // ------------------------------------------------------------ producer of chain (warp - 18)
-        if (lane == 0) {
-            const int c = warp - 18;
+    if (warp == 18) {
+        // ------------------------------------------------------------ producers: lane c feeds chain c
+        if (lane < 2) {
+            const int c = lane;
             if (c == 0) {
                 mbar_expect_tx(w_bar, Cfg::kWBytes);
                 const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
@@ -1570,11 +1575,17 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
-                            float z[4], r[4];
+                            float r[4];
                             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + c0 + i);
+#ifndef CF_PRECISE_ACT
+                            r[0] = sigmoid_zb(__uint_as_float(ar[c0 + i]), b4.x); r[1] = sigmoid_zb(__uint_as_float(ar[c0 + i + 1]), b4.y);
+                            r[2] = sigmoid_zb(__uint_as_float(ar[c0 + i + 2]), b4.z); r[3] = sigmoid_zb(__uint_as_float(ar[c0 + i + 3]), b4.w);
+#else
+                            float z[4];
                             z[0] = __uint_as_float(ar[c0 + i]) + b4.x; z[1] = __uint_as_float(ar[c0 + i + 1]) + b4.y;
                             z[2] = __uint_as_float(ar[c0 + i + 2]) + b4.z; z[3] = __uint_as_float(ar[c0 + i + 3]) + b4.w;
                             sigmoid4_z(z, r);
+#endif
                             split_bf16x2(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
                             split_bf16x2(r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
                         }
@@ -1595,11 +1606,16 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        float z[4];
                         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + kH + j0 + i);
+#ifndef CF_PRECISE_ACT
+                        u[i] = sigmoid_zb(__uint_as_float(au[i]), b4.x); u[i + 1] = sigmoid_zb(__uint_as_float(au[i + 1]), b4.y);
+                        u[i + 2] = sigmoid_zb(__uint_as_float(au[i + 2]), b4.z); u[i + 3] = sigmoid_zb(__uint_as_float(au[i + 3]), b4.w);
+#else
+                        float z[4];
                         z[0] = __uint_as_float(au[i]) + b4.x; z[1] = __uint_as_float(au[i + 1]) + b4.y;
                         z[2] = __uint_as_float(au[i + 2]) + b4.z; z[3] = __uint_as_float(au[i + 3]) + b4.w;
                         sigmoid4_z(z, u + i);
+#endif
                     }
                 }
                 // ---- candidate, new state h = c + u (h - c)
@@ -1618,11 +1634,17 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    float z[4], cv[4];
+                    float cv[4];
                     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * kH + j0 + i);
+#ifndef CF_PRECISE_ACT
+                    cv[0] = tanh_zb(__uint_as_float(ac[i]), b4.x); cv[1] = tanh_zb(__uint_as_float(ac[i + 1]), b4.y);
+                    cv[2] = tanh_zb(__uint_as_float(ac[i + 2]), b4.z); cv[3] = tanh_zb(__uint_as_float(ac[i + 3]), b4.w);
+#else
+                    float z[4];
                     z[0] = __uint_as_float(ac[i]) + b4.x; z[1] = __uint_as_float(ac[i + 1]) + b4.y;
                     z[2] = __uint_as_float(ac[i + 2]) + b4.z; z[3] = __uint_as_float(ac[i + 3]) + b4.w;
                     tanh4_z(z, cv);
+#endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
                     split_bf16x2(h[i], h[i + 1], hi[i >> 1], lo[i >> 1]);
@@ -1824,10 +1846,10 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     }
                     const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
                     if (L.in == kC)
-                        tc_gru_fused2_kernel<32><<<grid2, 640, GruF2Cfg<32>::kSmem, stream>>>(
+                        tc_gru_fused2_kernel<32><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
                             L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth, nullptr);
                     else
-                        tc_gru_fused2_kernel<128><<<grid2, 640, GruF2Cfg<128>::kSmem, stream>>>(
+                        tc_gru_fused2_kernel<128><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
                             L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth,
                             trace_dev);
                     CF_LAUNCHED();

@@ -307,6 +307,14 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Fused "bias + activation" on exponent-domain accumulators: y = act(acc + b).
+// With MUFU.TANH the bias add folds into the argument scaling (one FFMA): callers pass bk = b * k.
+#ifndef CF_PRECISE_ACT
+constexpr float kSigArgScale = -0.34657359027997264f;     // z * (-ln2 / 2): sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
+constexpr float kTanhArgScale = 0.34657359027997264f;      // z * ( ln2 / 2): tanh(x)
+__device__ __forceinline__ float sigmoid_zb(float acc, float bk) { return fmaf(tanh_approx(fmaf(acc, kSigArgScale, bk)), 0.5f, 0.5f); }
+__device__ __forceinline__ float tanh_zb(float acc, float bk) { return tanh_approx(fmaf(acc, kTanhArgScale, bk)); }
+#endif
 #ifndef CF_PRECISE_ACT
 // Default: MUFU.TANH based activations, one MUFU + one FMA-pipe instruction per gate value.
 // Measured end to end on B200 (tools/accuracy_check.py, 240 000 positions, shipped weights):
