@@ -254,7 +254,7 @@ __global__ void tc_pack_a_kernel(const float* __restrict__ in, int K, int64_t n_
 // Each round is: operands to smem -> one thread issues the MMAs -> commit -> all threads run the
 // TMEM epilogue for their own window (thread = TMEM lane = window).
 constexpr uint32_t kSliceBytes = 2u * 128 * kC * 2;       // one position of a tile as A operand: 16 KB
-constexpr uint32_t kConvSmem = ConvParams::kBytes + 9 * kSliceBytes + 35 * 128 * 4 + 256;
+constexpr uint32_t kConvSmem = ConvParams::kBytes + 10 * kSliceBytes + 35 * 128 * 4 + 256;   // tc_conv2: O1 ring of 4
 
 __device__ __forceinline__ void store_a_row32(uint8_t* slice, int row, const float* v) {
     // 32 channels of one window into an operand slice {hi, lo} x [4][128][8]
@@ -506,8 +506,8 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* prm = smem;
-    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 3 slices
-    uint8_t* o2 = o1 + 3 * kSliceBytes;
+    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 4 slices (o1 is produced two positions ahead)
+    uint8_t* o2 = o1 + 4 * kSliceBytes;
     uint8_t* y0 = o2 + kSliceBytes;
     uint8_t* p1 = y0 + kSliceBytes;                   // ring of 3 slices
     uint8_t* p2 = p1 + 3 * kSliceBytes;
@@ -553,7 +553,7 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     for (int tap = 0; tap < 3; ++tap) {
                         const int tt = t1 + tap - 1;
                         if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_pred<32>(tmem + 0, o1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
+                        conv_mma_pred<32>(tmem + 0, o1_u + (tt & 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
                         first = false;
                     }
                 }
@@ -597,7 +597,7 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
-            store_a_row16(o1 + (t % 3) * kSliceBytes, row, c0, v);
+            store_a_row16(o1 + (t & 3) * kSliceBytes, row, c0, v);
         };
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -618,6 +618,7 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             make_o1(0);
+            make_o1(1);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncwarp();
@@ -652,18 +653,20 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 }
                 if (h3) { relu_bias(r3, 7, v); store_a_row16(p1 + (t3 % 3) * kSliceBytes, row, c0, v); }   // b5
                 if (h4) { relu_bias(r4, 8, v); store_a_row16(p2, row, c0, v); }                  // b6
+                // operands of the next MMA batch are complete: hand over, then finish the work the
+                // issuer does not wait for (block output y1[u-6], o1 two positions ahead)
+                if (u < kLastU) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ready);
+                }
                 if (h5) {
                     relu_bias(r5, 9, v);                                                         // b7
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + (__uint_as_float(rs[i]) + fp[192 + c0 + i]), 0.f);   // + sc1 + b4
                     store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
                 }
-                if (u + 1 < kWindow) make_o1(u + 1);
-                if (u < kLastU) {
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_ready);
-                }
+                if (u + 2 < kWindow) make_o1(u + 2);
             }
         }
     }
