@@ -183,3 +183,30 @@ def test_ultra_long_read_vs_oracle(shipped_weights):
     assert lengths[0] == want_len == 1_000_000
     assert np.abs(scores[0] - want_scores).max() < PROB_TOL
     _check_intervals(hps[0], scores[0], want_scores)
+
+
+def test_random_init_resnetrnn_outliers_and_parameters():
+    """Different weights (seeded Glorot draw), signal with spikes spanning the int16 range, and the
+    non-default post-processing parameters through the batched entry point."""
+    w = weights.random_init("ResNetRNN", seed=5)
+    m = _model("ResNetRNN", "auto", w)
+    graph = tf_graph.TorchGraph(w)
+    rng = np.random.default_rng(12)
+    reads = synth.synth_reads([5000, 7777, 3500], base_seed=880)
+    spiky = reads[1].copy()
+    spiky[rng.integers(0, len(spiky), size=40)] = rng.choice([-32768, 32767, 0, 8191], size=40)
+    reads[1] = spiky
+    hps, lens, scores = infer.infer_reads(reads, m, return_scores=True)
+    for r, h, s in zip(reads, hps, scores):
+        want_h, _, want_s = postprocess.infer_read(r, graph.infer)
+        assert np.abs(s - want_s).max() < PROB_TOL
+        _check_intervals(h, s, want_s)
+    # non-default threshold / min_run / extensions
+    m2 = _model("ResNetRNN", "auto")
+    reads2 = synth.synth_reads([9000, 4000], base_seed=41)
+    for thr, min_run, el, er in ((0.9, 15, 11, 16), (0.3, 5, 0, 0), (0.5, 40, 3, 7)):
+        hps2, _, sc2 = infer.infer_reads(reads2, m2, threshold=thr, min_run=min_run, extension_left=el,
+                                         extension_right=er, return_scores=True)
+        for h, s in zip(hps2, sc2):
+            labels = postprocess.correct_short(postprocess.class_from_threshold(s.astype(np.float64), thr), min_run)
+            assert h == postprocess.hp_in_pred(labels, el, er)
