@@ -32,7 +32,7 @@ using namespace ptx;
 constexpr int kH = 64;            // GRU units
 constexpr int kC = 32;            // conv channels
 constexpr int kNX = 3 * kH;       // 192 projection columns per direction (r | u | c)
-constexpr int kTcChunkTiles = 592;   // tiles per internal pass (4 waves of 148 CTAs)
+constexpr int kTcChunkTiles = 1184;  // tiles per internal pass (8 tiles per chain of the GRU kernel)
 constexpr float kGateScale = -1.4426950408889634f;    // -log2(e)
 constexpr float kCandScale = 2.8853900817779268f;     // 2 log2(e)
 
@@ -1690,28 +1690,36 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #undef CF_TR
 
 // ====================================================================== TK5: head
-// p = sigmoid(part_fw + part_bw + b), scattered to sample order with the padding cut (infer.py:47).
-__global__ void tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const int64_t* __restrict__ src,
-                               const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
-                               const double* __restrict__ stats, int64_t tile0, int64_t n_rows,
-                               float* __restrict__ probs) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, w, t) with t fastest
-    if (i >= n_rows) return;
-    const int t = (int)(i % kWindow);
-    const int64_t wi = i / kWindow;
-    const int w = (int)(wi % kTileWindows);
-    const int64_t tile = wi / kTileWindows;
-    const int64_t g = (tile0 + tile) * kTileWindows + w;
-    if (t >= valid[g]) return;
-    const size_t blk = (size_t)tile * kWindow + t;
-    float acc = b;
-    for (int k = 0; k < n_parts; ++k) acc += head_part[(blk * n_parts + k) * 128 + w];
-    float p = 1.f / (1.f + expf(-acc));
-    if (stats) {
-        const double sc = stats[2 * read[g] + 1];
-        if (!(sc > 0.0)) p = nanf("");
+// p = sigmoid(sum of the partial dots + b), scattered to sample order with the padding cut
+// (infer.py:47).  One CTA per tile: the partials are read window-fastest (coalesced), transposed
+// through shared memory, and the probabilities are written position-fastest, which is contiguous in
+// the read because consecutive windows of a read are consecutive in the signal.
+__global__ void __launch_bounds__(256)
+tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const int64_t* __restrict__ src,
+               const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
+               const double* __restrict__ stats, int64_t tile0, int64_t n_rows, float* __restrict__ probs) {
+    __shared__ float logit[kWindow][kTileWindows + 1];
+    const int64_t tile = blockIdx.x;
+    if (tile * kTileWindows * kWindow >= n_rows) return;
+    for (int i = threadIdx.x; i < kWindow * kTileWindows; i += blockDim.x) {
+        const int t = i / kTileWindows, w = i % kTileWindows;
+        const size_t blk = (size_t)tile * kWindow + t;
+        float acc = b;
+        for (int k = 0; k < n_parts; ++k) acc += head_part[(blk * n_parts + k) * 128 + w];
+        logit[t][w] = acc;
     }
-    probs[src[g] + t] = p;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWindow * kTileWindows; i += blockDim.x) {
+        const int w = i / kWindow, t = i % kWindow;
+        const int64_t g = (tile0 + tile) * kTileWindows + w;
+        if (t >= valid[g]) continue;
+        float p = 1.f / (1.f + expf(-logit[t][w]));
+        if (stats) {
+            const double sc = stats[2 * read[g] + 1];
+            if (!(sc > 0.0)) p = nanf("");
+        }
+        probs[src[g] + t] = p;
+    }
 }
 
 // ResNet-only head (resnet_class.py:23 commented out): dense 32 -> 1 + sigmoid straight from the
@@ -1927,7 +1935,7 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             CF_LAUNCHED();
         } else {
             ProfScope ps(prof, KC_K5_HEAD, stream);
-            tc_head_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
+            tc_head_kernel<<<(unsigned)tiles, 256, 0, stream>>>(
                 head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);
             CF_LAUNCHED();
         }
