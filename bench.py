@@ -101,7 +101,7 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for ts, r in self.rows if t0 <= ts <= t1] or [r for _, r in self.rows]
         for r in rows:
@@ -111,13 +111,22 @@ class ClockSampler(object):
             try:
                 sm.append(float(parts[0]))
                 smax.append(float(parts[1]))
+                power.append(float(parts[2]))
             except ValueError:
                 continue
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # "under load": samples taken while a kernel was running (power above half of the maximum seen);
+        # samples that fall into the host-side gap between steps show the idle clock
+        if power:
+            thr = 0.5 * max(power)
+            loaded = [c for c, p in zip(sm, power) if p >= thr] or sm
+        else:
+            loaded = sm
+        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(loaded),
+                "power_w_max": max(power) if power else None}
 
 
 def make_batch(n_reads, seed):
