@@ -13,20 +13,19 @@ from . import _cabi
 
 
 def center_hp(merged_positions, len_read, chunk_size=1000):
-    """catfish:121-135, in place on the last element (host helper; one interval of arithmetic)."""
-    m = merged_positions[-1]
-    len_hp = m[-1] - m[0]
-    if len_hp < chunk_size:
-        left_padding = (chunk_size - len_hp) // 2
-        right_padding = (chunk_size - len_hp) - left_padding
-        m[0] = m[0] - left_padding
-        m[1] = m[1] + right_padding
-        if m[0] < 0:
-            m[1] -= m[0]
-            m[0] = 0
-        if m[1] > len_read:
-            m[0] -= len_read - m[1]
-            m[1] = len_read
+    """catfish:121-135: pad the LAST chunk symmetrically up to ``chunk_size`` and keep it inside the
+    read (in place, host helper - one interval of integer arithmetic; the batched path is K7)."""
+    chunk = merged_positions[-1]
+    missing = chunk_size - (chunk[1] - chunk[0])
+    if missing > 0:
+        chunk[0] -= missing // 2
+        chunk[1] += missing - missing // 2
+        if chunk[0] < 0:                       # shift right so that the chunk starts at 0
+            chunk[1] -= chunk[0]
+            chunk[0] = 0
+        if chunk[1] > len_read:                # the reference moves the START by the overflow here
+            chunk[0] -= len_read - chunk[1]
+            chunk[1] = len_read
     return merged_positions
 
 

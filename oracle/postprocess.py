@@ -71,18 +71,17 @@ def _runs(values):
 
 
 def correct_short_loops(predictions, threshold=15):
-    """infer.py:174-198."""
-    compressed = [[predictions[0], 0]]
-    for p in predictions:
-        if p == compressed[-1][0]:
-            compressed[-1][1] += 1
+    """infer.py:174-198, element by element: run-length encode, zero the short non-zero runs, expand."""
+    runs = []                                   # [label, length]
+    first = predictions[0]                      # IndexError on empty input, like the reference
+    del first
+    for label in predictions:
+        if runs and runs[-1][0] == label:
+            runs[-1][1] += 1
         else:
-            compressed.append([p, 1])
-    for ci, c in enumerate(compressed):
-        if c[0] != 0:
-            if c[1] < threshold:
-                compressed[ci][0] = 0
-    return np.concatenate([np.repeat(c[0], c[1]) for c in compressed])
+            runs.append([label, 1])
+    pieces = [np.repeat(0 if (label != 0 and length < threshold) else label, length) for label, length in runs]
+    return np.concatenate(pieces)
 
 
 def correct_short(predictions, threshold=15):
@@ -92,14 +91,16 @@ def correct_short(predictions, threshold=15):
 
 
 def hp_in_pred_loops(predictions, extension_left=11, extension_right=16, label=1):
-    """infer.py:141-162."""
-    compressed = [[predictions[0], 0, 0]]
-    for p in range(len(predictions)):
-        if predictions[p] == compressed[-1][0]:
-            compressed[-1][1] += 1
-        else:
-            compressed.append([predictions[p], 1, p])
-    return [[c[2] - extension_left, c[2] + c[1] + extension_right] for c in compressed if c[0] == label]
+    """infer.py:141-162, element by element: (label, start, length) of every run, keep those of ``label``."""
+    predictions[0]                              # IndexError on empty input, like the reference
+    out = []
+    start = 0
+    for pos in range(1, len(predictions) + 1):
+        if pos == len(predictions) or predictions[pos] != predictions[start]:
+            if predictions[start] == label:
+                out.append([start - extension_left, pos + extension_right])      # start + length = pos
+            start = pos
+    return out
 
 
 def hp_in_pred(predictions, extension_left=11, extension_right=16, label=1):

@@ -126,3 +126,31 @@ def test_shims():
             spec.loader.exec_module(m)
             ours = getattr({"compute_on_read": compute_on_read, "output_homopolymers": output_homopolymers}[mod], fn)
             assert ours(*args) == getattr(m, fn)(*args)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the product package may reference it."""
+    pkg = os.path.join(ROOT, "catfish_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+                assert "oracle." not in text.replace("oracle.tf_graph", "").replace("oracle/", "") or fn.endswith(".md"), fn
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device every compute entry point raises instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from catfish_b200 import infer
+    for call in (lambda: infer.normalize_raw_signal(np.array([1, 2, 3], np.int16), "median"),
+                 lambda: infer.class_from_threshold([0.1, 0.9]),
+                 lambda: infer.correct_short([1, 1, 0]),
+                 lambda: infer.hp_in_pred([1, 1, 0])):
+        with pytest.raises(_cabi.CatfishError):
+            call()
+    m = neural_network.build_model("ResNetRNN", **weights.SHIPPED_HPARAMS)
+    with pytest.raises(_cabi.CatfishError):
+        m.set_weights(weights.load_shipped())            # cf_model_create -> CF_ERR_NO_DEVICE
