@@ -512,6 +512,28 @@ int cf_merge_chunks(int32_t device, const int64_t* intervals_dev, const int64_t*
     return s;
 }
 
+int cf_split_raw(int32_t device, const int16_t* raw_dev, const int64_t* offsets_host, int32_t n_reads,
+                 const int64_t* ranges_dev, const int32_t* range_read_dev, int64_t n_ranges, int16_t* out_dev,
+                 int64_t capacity, int64_t* piece_offsets_dev, void* stream) {
+    if (n_reads < 0 || n_ranges < 0 || !offsets_host || !piece_offsets_dev || capacity < 0 ||
+        (n_ranges > 0 && (!raw_dev || !ranges_dev || !range_read_dev)) || (capacity > 0 && !out_dev)) {
+        cf::set_error("cf_split_raw: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    CF_TRY(cf::use_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TempBufs tmp;
+    cf::DevBuf* off = tmp.make();
+    cf::DevBuf* len = tmp.make();
+    if (n_reads > 0) CF_TRY(upload_offsets(offsets_host, n_reads, off, st));
+    CF_TRY(len->ensure(sizeof(int64_t) * (size_t)(n_ranges + 1)));
+    const int16_t* raw0 = n_reads > 0 ? raw_dev + offsets_host[0] : raw_dev;
+    int s = cf::k8_split_raw(raw0, off->as<int64_t>(), ranges_dev, range_read_dev, n_ranges, len->as<int64_t>(),
+                             piece_offsets_dev, capacity, out_dev, st);
+    cudaStreamSynchronize(st);
+    return s;
+}
+
 int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int32_t k, const float* wx_host,
                       const float* bias_host, float* out_dev, void* stream) {
     if (!a_dev || !wx_host || !bias_host || !out_dev || n_blocks <= 0) { cf::set_error("cf_selftest_xproj: bad argument"); return CF_ERR_BAD_ARG; }

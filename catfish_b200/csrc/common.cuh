@@ -169,4 +169,9 @@ int k7_merge_chunks(int64_t* work, const int64_t* ioff, const int64_t* read_len,
                     int32_t* idx, int64_t* merged, int64_t* merged_cnt, int64_t* nonhp, int64_t* nonhp_cnt,
                     cudaStream_t stream);
 
+// ---------------------------------------------------------------- k8: signal slicing (next row N2)
+int k8_split_raw(const int16_t* raw, const int64_t* offsets_dev, const int64_t* ranges, const int32_t* range_read,
+                 int64_t n_ranges, int64_t* lengths_scratch, int64_t* piece_off, int64_t capacity, int16_t* out,
+                 cudaStream_t stream);
+
 }  // namespace cf

@@ -202,6 +202,22 @@ int cf_merge_chunks(int32_t device, const int64_t* intervals_dev, const int64_t*
                     int64_t* merged_count_dev, int64_t* nonhp_dev, int64_t* nonhp_count_dev, void* stream);
 
 /*
+ * cf_split_raw - "next" row N2: the computation inside split_f5.split_signal
+ * (catfish/split_f5.py:36,64: `new_signal = signal_dset[s[0] : s[1]]`) for a batch of ranges.
+ *   raw_dev / offsets_host [n_reads+1] : the reads, concatenated int16 on the device
+ *   ranges_dev int64 [n_ranges][2], range_read_dev int32 [n_ranges] : (start, end) in read-local
+ *                 coordinates and the read each range cuts; numpy slice semantics (negative bounds count
+ *                 from the end, bounds clamp to the read, inverted ranges are empty)
+ *   out_dev int16 [capacity] : the pieces, concatenated in range order
+ *   piece_offsets_dev int64 [n_ranges+1] : start of every piece in out_dev; last element = total
+ * Pieces that would exceed `capacity` are truncated (compare the total with capacity).  Synchronises.
+ * HDF5 / gzip writing of the pieces stays on the host.
+ */
+int cf_split_raw(int32_t device, const int16_t* raw_dev, const int64_t* offsets_host, int32_t n_reads,
+                 const int64_t* ranges_dev, const int32_t* range_read_dev, int64_t n_ranges, int16_t* out_dev,
+                 int64_t capacity, int64_t* piece_offsets_dev, void* stream);
+
+/*
  * cf_selftest_xproj - unit self-test of the tcgen05 GEMM path (no reference counterpart): the GRU
  * input projection out[blk][n][w] = sum_k a[blk*128 + w][k] * wx[k][n] + bias[n], n in [0, 384),
  * through the engine's operand packing, bulk (TMA) copies, tcgen05.mma and TMEM epilogue.
