@@ -357,6 +357,8 @@ int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const d
             }
             float* yout = (l & 1) ? b.y1 : b.y0;
             const size_t smem = sizeof(float) * 2 * 32 * (H + 1);
+            if (smem > 48 * 1024)      // H > ~190: opt in to the larger dynamic shared memory carve-out
+                CF_CUDA(cudaFuncSetAttribute(simt_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
                 ProfScope ps(prof, KC_K4_GRU, stream);
                 simt_gru_kernel<<<dim3((unsigned)tiles, 4, 2), 256, smem, stream>>>(

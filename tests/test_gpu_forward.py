@@ -210,3 +210,17 @@ def test_random_init_resnetrnn_outliers_and_parameters():
         for h, s in zip(hps2, sc2):
             labels = postprocess.correct_short(postprocess.class_from_threshold(s.astype(np.float64), thr), min_run)
             assert h == postprocess.hp_in_pred(labels, el, er)
+
+
+def test_rnn_stress_variant_h256_five_layers_simt():
+    """The reference's commented "RNN" search setting (train_validate.py:330): H = 256, 5 layers.  Not a
+    tcgen05 shape: runs on the fp32 SIMT engine, still through the same C ABI."""
+    hpm = dict(layer_size=256, n_layers=5)
+    w = weights.random_init("RNN", seed=31, **hpm)
+    m = _model("RNN", "auto", w, **hpm)
+    assert m.resolved_engine == "simt"
+    rng = np.random.default_rng(5)
+    x = rng.normal(0, 1.5, size=(70, 35, 1)).astype(np.float32)
+    got = m.infer(x)
+    want = tf_graph.forward_np(w, x, np.float64)
+    assert np.abs(got - want).max() < PROB_TOL

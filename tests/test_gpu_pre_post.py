@@ -141,3 +141,20 @@ def test_python_helpers_match_golden():
         lab = random_labels(rng, n) * rng.integers(1, 4, size=n)          # multi-valued labels
         np.testing.assert_array_equal(infer.correct_short(lab, thr), postprocess.correct_short(lab, thr))
         assert infer.hp_in_pred(lab, label=2) == postprocess.hp_in_pred(lab, label=2)
+
+
+def test_interval_calling_property_based():
+    """hypothesis: arbitrary small label patterns, thresholds and run lengths against the loop oracle."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.lists(st.integers(0, 1), min_size=1, max_size=200), min_size=1, max_size=6),
+           st.integers(1, 40), st.integers(0, 20), st.integers(0, 20))
+    def check(label_lists, min_run, ext_left, ext_right):
+        probs = [np.where(np.array(l) == 1, 0.75, 0.25).astype(np.float32) for l in label_lists]
+        got = _call_intervals(probs, np.float32, min_run=min_run, ext_left=ext_left, ext_right=ext_right)
+        for l, g in zip(label_lists, got):
+            labels = postprocess.correct_short_loops(list(l), min_run)
+            assert g == postprocess.hp_in_pred_loops(list(labels), ext_left, ext_right)
+
+    check()
