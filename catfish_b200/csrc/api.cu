@@ -250,6 +250,7 @@ struct cf_model {
     cf::DevBuf stats, wide_flags, wide_scratch, k1_chunked, k1_chunk_tab;
     cf::DevBuf tab_src, tab_valid, tab_read;
     cf::DevBuf probs_internal;
+    cf::DevBuf val_logits, val_partial;   // validation row (N4)
     cf::IntervalScratch k6;
     cf::Profiler prof;
     // host-buffer entry point
@@ -280,10 +281,11 @@ static int use_device(int device) {
 }
 
 static int engine_forward(cf_model* m, const int16_t* raw, const double* stats, const float* xwin,
-                          WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream) {
+                          WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream,
+                          bool want_logits = false) {
     if (m->engine == CF_ENGINE_TCGEN05)
-        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof);
-    return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof);
+        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits);
+    return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits);
 }
 
 // Validate offsets and lay out the windows of every read (infer.py:32-43).
@@ -671,6 +673,89 @@ int cf_infer_windows(cf_model* m, const float* x_dev, int64_t n_windows, float* 
     cf::dense_window_table_kernel<<<(unsigned)cf::ceil_div(slots, 256), 256, 0, st>>>(n_windows, slots, tab.src, tab.valid, tab.read);
     CF_LAUNCHED();
     return cf::engine_forward(m, nullptr, nullptr, x_dev, tab, tiles, probs_dev, st);
+}
+
+int cf_validate_windows(cf_model* m, const float* x_dev, const uint8_t* labels_dev, int64_t n_windows,
+                        int64_t padding_size, double threshold, int64_t* counts_out, double* accuracy_out,
+                        double* loss_out, void* stream) {
+    if (!m || n_windows <= 0 || !x_dev || !labels_dev || padding_size < 0 || !counts_out) {
+        cf::set_error("cf_validate_windows: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    std::lock_guard<std::mutex> lock(m->mu);
+    CF_TRY(cf::use_device(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n = n_windows * cf::kWindow;
+    const int64_t tiles = cf::ceil_div(n_windows, cf::kTileWindows);
+    const int blocks = cf::k9_validation_blocks(n);
+    CF_TRY(m->val_logits.ensure(sizeof(float) * (size_t)n));
+    CF_TRY(m->val_partial.ensure(sizeof(long long) * 6 * ((size_t)blocks + 1)));
+    cf::WindowTable tab;
+    CF_TRY(cf::ensure_table(m, tiles, &tab));
+    const int64_t slots = tiles * cf::kTileWindows;
+    cf::dense_window_table_kernel<<<(unsigned)cf::ceil_div(slots, 256), 256, 0, st>>>(n_windows, slots, tab.src, tab.valid, tab.read);
+    CF_LAUNCHED();
+    CF_TRY(cf::engine_forward(m, nullptr, nullptr, x_dev, tab, tiles, m->val_logits.as<float>(), st, /*want_logits=*/true));
+    long long* partial = m->val_partial.as<long long>();
+    long long* result = partial + (size_t)blocks * 6;
+    CF_TRY(cf::k9_validate(m->val_logits.as<float>(), labels_dev, n, threshold, partial, result, st));
+    long long host[6];
+    CF_CUDA(cudaMemcpyAsync(host, result, sizeof(host), cudaMemcpyDeviceToHost, st));
+    CF_CUDA(cudaStreamSynchronize(st));
+    counts_out[0] = host[0];
+    counts_out[1] = host[1];
+    counts_out[2] = host[2] - padding_size;      // rnn_class.py:247
+    counts_out[3] = host[3];
+    double loss_sum;
+    std::memcpy(&loss_sum, &host[5], sizeof(double));
+    if (accuracy_out) *accuracy_out = (double)host[4] / (double)n;
+    if (loss_out) *loss_out = loss_sum / (double)n;
+    return CF_OK;
+}
+
+int cf_vote_events(int32_t device, const double* scores_dev, int64_t n_scores, const int64_t* event_lengths_host,
+                   int64_t n_events, int64_t start, int64_t length, int32_t* classes_dev, int64_t* n_voted_out,
+                   int64_t* start_event_out, int64_t* final_event_out, int32_t* empty_event_out, void* stream) {
+    if (n_scores < 0 || n_events < 0 || (n_events > 0 && !event_lengths_host) || (n_scores > 0 && !scores_dev) ||
+        !n_voted_out || !start_event_out || !final_event_out) {
+        cf::set_error("cf_vote_events: bad argument");
+        return CF_ERR_BAD_ARG;
+    }
+    // the control flow of the reference's loop (networks/correct_output.py:43-61) on the scanned lengths
+    std::vector<int64_t> begin((size_t)n_events + 1, 0);
+    int64_t start_event = -1, final_event = -2, n_voted = 0, summed = 0;
+    for (int64_t n = 0; n < n_events; ++n) {
+        begin[n] = summed;
+        if (start_event < 0 && summed >= start) start_event = n;
+        summed += event_lengths_host[n];
+        begin[n + 1] = summed;
+        if (summed > length) { final_event = n - 1; break; }
+        if (start_event >= 0) {
+            ++n_voted;
+            if (summed == start + length) { final_event = n; break; }
+        }
+    }
+    *n_voted_out = n_voted;
+    *start_event_out = start_event;
+    *final_event_out = final_event;
+    if (empty_event_out) *empty_event_out = 0;
+    if (n_voted == 0) return CF_OK;
+    if (!classes_dev) { cf::set_error("cf_vote_events: classes_dev is NULL"); return CF_ERR_BAD_ARG; }
+    CF_TRY(cf::use_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TempBufs tmp;
+    cf::DevBuf* ev = tmp.make();
+    cf::DevBuf* flag = tmp.make();
+    CF_TRY(ev->ensure(sizeof(int64_t) * (size_t)(n_voted + 1)));
+    CF_TRY(flag->ensure(sizeof(int32_t)));
+    CF_CUDA(cudaMemcpyAsync(ev->ptr, begin.data() + start_event, sizeof(int64_t) * (size_t)(n_voted + 1),
+                            cudaMemcpyHostToDevice, st));
+    CF_TRY(cf::k10_vote_events(scores_dev, n_scores, ev->as<int64_t>(), 0, n_voted, classes_dev, flag->as<int32_t>(), st));
+    int32_t empty = 0;
+    CF_CUDA(cudaMemcpyAsync(&empty, flag->ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CF_CUDA(cudaStreamSynchronize(st));
+    if (empty_event_out) *empty_event_out = empty;
+    return CF_OK;
 }
 
 int cf_infer_reads(cf_model* m, const int16_t* raw_dev, const int64_t* offsets_host, int32_t n_reads,

@@ -174,4 +174,14 @@ int k8_split_raw(const int16_t* raw, const int64_t* offsets_dev, const int64_t* 
                  int64_t n_ranges, int64_t* lengths_scratch, int64_t* piece_off, int64_t capacity, int16_t* out,
                  cudaStream_t stream);
 
+// ---------------------------------------------------------------- k9: validation counts (next row N4)
+int k9_validation_blocks(int64_t n);
+// partial: int64 [k9_validation_blocks(n)][6]; result: tp, fp, tn, fn, correct (int64) | loss sum (double)
+int k9_validate(const float* logits, const uint8_t* labels, int64_t n, double threshold, long long* partial,
+                long long* result, cudaStream_t stream);
+
+// ---------------------------------------------------------------- k10: event voting (next row N3)
+int k10_vote_events(const double* scores, int64_t n_scores, const int64_t* ev_begin, int64_t first_event,
+                    int64_t n_voted, int32_t* classes, int32_t* empty_flag, cudaStream_t stream);
+
 }  // namespace cf

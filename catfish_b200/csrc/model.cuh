@@ -51,10 +51,11 @@ SimtEngine* simt_create(const HostModel& hm);
 void simt_destroy(SimtEngine* e);
 // Forward pass over n_tiles tiles of 128 windows.  Input is either the raw int16 signal with
 // per-read (shift, scale) or already-normalised float windows; output probabilities are
-// scattered to probs[tab.src[g] + t] for t < tab.valid[g].
+// scattered to probs[tab.src[g] + t] for t < tab.valid[g].  With want_logits the dense layer's output
+// (rnn_class.py:178-183) is written instead of its sigmoid - the validation row needs it for the loss.
 int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                  const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-                 cudaStream_t stream, Profiler* prof);
+                 cudaStream_t stream, Profiler* prof, bool want_logits = false);
 
 // ---------------------------------------------------------------- tcgen05 engine
 struct TcEngine;
@@ -63,7 +64,7 @@ TcEngine* tc_create(const HostModel& hm);
 void tc_destroy(TcEngine* e);
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-               cudaStream_t stream, Profiler* prof);
+               cudaStream_t stream, Profiler* prof, bool want_logits = false);
 
 int tc_selftest_xproj(const float* a_dev, int64_t n_blocks, int K, const float* wx_host, const float* bias_host,
                       float* out_dev, cudaStream_t stream);

@@ -246,7 +246,7 @@ simt_gru_kernel(const float* __restrict__ xp, const float* __restrict__ wgh_fw,
 __global__ void simt_head_kernel(const float* __restrict__ y, const float* __restrict__ w, float b, int F,
                                  const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
                                  const int32_t* __restrict__ read, const double* __restrict__ stats,
-                                 int64_t tile0, int64_t n_rows, float* __restrict__ probs) {
+                                 int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits) {
     // thread i handles (window, t) with t fastest so that the scatter is coalesced
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
@@ -259,7 +259,7 @@ __global__ void simt_head_kernel(const float* __restrict__ y, const float* __res
     const float* yr = y + ((tile * kWindow + t) * kTileWindows + w_in) * (int64_t)F;
     float acc = b;
     for (int k = 0; k < F; ++k) acc = fmaf(yr[k], w[k], acc);
-    float p = 1.f / (1.f + expf(-acc));
+    float p = want_logits ? acc : 1.f / (1.f + expf(-acc));
     if (stats) {                                         // scale == 0 or NaN: the reference divides by it
         const double sc = stats[2 * read[g] + 1];
         if (!(sc > 0.0)) p = nanf("");
@@ -333,7 +333,7 @@ int simt_conv_stack(SimtEngine* e, const HostModel& hm, const int16_t* raw, cons
 
 int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                  const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-                 cudaStream_t stream, Profiler* prof) {
+                 cudaStream_t stream, Profiler* prof, bool want_logits) {
     if (n_tiles <= 0) return CF_OK;
     const int64_t chunk = n_tiles < kSimtChunkTiles ? n_tiles : kSimtChunkTiles;
     SimtBufs b;
@@ -371,7 +371,7 @@ int simt_forward(SimtEngine* e, const HostModel& hm, const int16_t* raw, const d
         ProfScope ps(prof, KC_K5_HEAD, stream);
         simt_head_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
             hin, e->head_w, e->head_b, hm.head_features(), tab.src, tab.valid, tab.read, raw ? stats : nullptr,
-            tile0, rows, probs);
+            tile0, rows, probs, want_logits ? 1 : 0);
         CF_LAUNCHED();
     }
     return CF_OK;

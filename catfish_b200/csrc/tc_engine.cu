@@ -1697,7 +1697,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const int64_t* __restrict__ src,
                const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
-               const double* __restrict__ stats, int64_t tile0, int64_t n_rows, float* __restrict__ probs) {
+               const double* __restrict__ stats, int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits) {
     __shared__ float logit[kWindow][kTileWindows + 1];
     const int64_t tile = blockIdx.x;
     if (tile * kTileWindows * kWindow >= n_rows) return;
@@ -1713,7 +1713,7 @@ tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const 
         const int w = i / kWindow, t = i % kWindow;
         const int64_t g = (tile0 + tile) * kTileWindows + w;
         if (t >= valid[g]) continue;
-        float p = 1.f / (1.f + expf(-logit[t][w]));
+        float p = want_logits ? logit[t][w] : 1.f / (1.f + expf(-logit[t][w]));
         if (stats) {
             const double sc = stats[2 * read[g] + 1];
             if (!(sc > 0.0)) p = nanf("");
@@ -1727,7 +1727,7 @@ tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const 
 __global__ void tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ w, float b,
                                     const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
                                     const int32_t* __restrict__ read, const double* __restrict__ stats,
-                                    int64_t tile0, int64_t n_rows, float* __restrict__ probs) {
+                                    int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, w, t) with t fastest
     if (i >= n_rows) return;
     const int t = (int)(i % kWindow);
@@ -1751,7 +1751,7 @@ __global__ void tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const f
             acc = fmaf(v1, __ldg(w + kg * 8 + 2 * k + 1), acc);
         }
     }
-    float p = 1.f / (1.f + expf(-acc));
+    float p = want_logits ? acc : 1.f / (1.f + expf(-acc));
     if (stats) {
         const double sc = stats[2 * read[g] + 1];
         if (!(sc > 0.0)) p = nanf("");
@@ -1775,7 +1775,7 @@ static size_t tc_workspace_bytes(const HostModel& hm, int64_t tiles) {
 }
 
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats, const float* xwin,
-               WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream, Profiler* prof) {
+               WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream, Profiler* prof, bool want_logits) {
     if (n_tiles <= 0) return CF_OK;
     if (!e->attr_done) {
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<32>::kSmem));
@@ -1931,12 +1931,12 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             // ResNet-only: dense on the conv output
             ProfScope ps(prof, KC_K5_HEAD, stream);
             tc_head_conv_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
-                a_in, e->head_w, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);
+                a_in, e->head_w, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs, want_logits ? 1 : 0);
             CF_LAUNCHED();
         } else {
             ProfScope ps(prof, KC_K5_HEAD, stream);
             tc_head_kernel<<<(unsigned)tiles, 256, 0, stream>>>(
-                head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs);
+                head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs, want_logits ? 1 : 0);
             CF_LAUNCHED();
         }
     }

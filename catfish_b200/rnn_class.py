@@ -3,8 +3,9 @@
 Reference: /root/reference/catfish/models/rnn_class.py (``RNN.__init__`` :10-54,
 ``restore_network`` :191-198, ``initialize_network`` :186-188, ``infer`` :213-219).
 Same constructor kwargs, attributes and return types; the TensorFlow graph and
-session are replaced by a handle of the C-ABI CUDA library.  Training
-(``train_network``, loss/optimizer, TensorBoard) is out of scope and raises.
+session are replaced by a handle of the C-ABI CUDA library.  ``test_network``
+follows the validation twin networks/rnn_class.py:222-261.  Training
+(``train_network``, optimizer, TensorBoard) is out of scope and raises.
 """
 
 import ctypes
@@ -136,8 +137,40 @@ class RNN(object):
     def train_network(self, *args, **kwargs):
         raise NotImplementedError("training is out of scope of catfish_b200 (inference hot path only)")
 
-    def test_network(self, *args, **kwargs):
-        raise NotImplementedError("validation metrics are out of scope of catfish_b200")
+    def test_network(self, test_x, test_y, read_name=None, file_path=None, padding_size=0, threshold=0.5):
+        """networks/rnn_class.py:222-261 ("next" row N4): forward pass + confusion counts.
+
+        ``test_x`` / ``test_y`` are the padded ``[n_windows, 35, 1]`` arrays of
+        ``train_validate.padding``; adds to ``self.tp/fp/tn/fn`` (true negatives minus
+        ``padding_size``, :247) and returns ``(test_acc, test_loss)`` over all positions,
+        padding included, like the reference's ``sess.run([self.accuracy, self.loss])``."""
+        import torch
+        x = np.ascontiguousarray(np.asarray(test_x, dtype=np.float32))
+        if x.ndim != 3 or x.shape[1] != self.window or x.shape[2] != self.n_inputs:
+            raise ValueError("Cannot feed value of shape %s for Tensor 'data/Placeholder:0', "
+                             "which has shape '(?, %d, %d)'" % (x.shape, self.window, self.n_inputs))
+        y = np.asarray(test_y).reshape(-1)
+        if y.size != x.shape[0] * self.window:
+            raise ValueError("Length of labels to compare is not equal.")
+        y8 = y.astype(np.uint8)
+        if not np.array_equal(y8, y):
+            raise ValueError("labels must be small non-negative integers")
+        n_windows = x.shape[0]
+        dev = torch.device("cuda", self.device)
+        counts = np.zeros(4, np.int64)
+        acc, loss = ctypes.c_double(), ctypes.c_double()
+        with torch.cuda.device(dev):
+            xd = torch.from_numpy(x.reshape(n_windows, self.window)).to(dev)
+            yd = torch.from_numpy(np.ascontiguousarray(y8)).to(dev)
+            stream = torch.cuda.current_stream(dev)
+            _cabi.check(_cabi.load_library().cf_validate_windows(
+                self.handle, xd.data_ptr(), yd.data_ptr(), n_windows, int(padding_size), float(threshold),
+                counts.ctypes.data_as(_cabi.c_i64_p), ctypes.byref(acc), ctypes.byref(loss), stream.cuda_stream))
+        self.tp += int(counts[0])
+        self.fp += int(counts[1])
+        self.tn += int(counts[2])
+        self.fn += int(counts[3])
+        return np.float32(acc.value), np.float32(loss.value)
 
     def _release(self):
         if getattr(self, "_handle", None) is not None:

@@ -218,6 +218,40 @@ int cf_split_raw(int32_t device, const int16_t* raw_dev, const int64_t* offsets_
                  int64_t capacity, int64_t* piece_offsets_dev, void* stream);
 
 /*
+ * cf_validate_windows - "next" row N4: one call of RNN.test_network (networks/rnn_class.py:222-261)
+ * without its file writing: forward pass over n_windows dense windows (padding included, as
+ * train_validate.padding :51-64 produced them), then on ALL n_windows*35 positions
+ *   pred = 1 if sigmoid(logit) >= threshold else 0                      (rnn_class.py:235)
+ *   counts_out[4] = tp, fp, tn - padding_size, fn                       (metrics.confusion_matrix,
+ *                   networks/trainingDB/metrics.py:10-37; the tn correction is rnn_class.py:247)
+ *   *accuracy_out = mean(round_half_even(sigmoid(logit)) == label)      (compute_accuracy :80-86)
+ *   *loss_out     = mean(max(z,0) - z*label + log1p(exp(-|z|)))         (compute_loss :72-77)
+ * x_dev float32 [n_windows][35] and labels_dev uint8 [n_windows*35] live on the device; the three
+ * outputs are host pointers (accuracy_out / loss_out may be NULL).  Synchronises.  The caller
+ * accumulates the counts over reads as the reference does in self.tp/fp/tn/fn (:244-248).
+ */
+int cf_validate_windows(cf_model* model, const float* x_dev, const uint8_t* labels_dev, int64_t n_windows,
+                        int64_t padding_size, double threshold, int64_t* counts_out, double* accuracy_out,
+                        double* loss_out, void* stream);
+
+/*
+ * cf_vote_events - "next" row N3: the arithmetic of correct_events (networks/correct_output.py:38-61,
+ * unfinished in the reference): walk the events as the reference's loop does (start found at the
+ * first event whose first measurement is >= start; stop before the event that would pass `length`,
+ * or after the one that ends at start + length) and give every visited event the class
+ * round_half_even(mean(scores[event begin : event end])).
+ *   scores_dev float64 [n_scores] (device); event_lengths_host int64 [n_events] (host)
+ *   classes_dev int32 [>= *n_voted_out] (device; n_events is always enough)
+ *   *start_event_out / *final_event_out : as the reference's variables; where the reference would
+ *                 leave them unbound, start_event is -1 and final_event is -2 (-1 is a legitimate
+ *                 final_event when the very first event already passes `length`); *empty_event_out != 0 when an event had no score (the
+ *                 reference divides by zero there).  Synchronises.
+ */
+int cf_vote_events(int32_t device, const double* scores_dev, int64_t n_scores, const int64_t* event_lengths_host,
+                   int64_t n_events, int64_t start, int64_t length, int32_t* classes_dev, int64_t* n_voted_out,
+                   int64_t* start_event_out, int64_t* final_event_out, int32_t* empty_event_out, void* stream);
+
+/*
  * cf_selftest_xproj - unit self-test of the tcgen05 GEMM path (no reference counterpart): the GRU
  * input projection out[blk][n][w] = sum_k a[blk*128 + w][k] * wx[k][n] + bias[n], n in [0, 384),
  * through the engine's operand packing, bulk (TMA) copies, tcgen05.mma and TMEM epilogue.
