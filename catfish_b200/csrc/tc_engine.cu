@@ -88,7 +88,8 @@ struct TcEngine {
     int n_sms = 148;
     bool attr_done = false;
     int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
-    int conv_variant = 2;             // 2 = one round per position (tc_conv2_kernel); 1 = three rounds (CF_TC_CONV=1)
+    int conv_variant = 4;             // 4 = two chains + k3 operands in TMEM (tc_conv4_kernel); 3 = two chains (tc_conv3_kernel, two residual blocks); 2 = one round per position
+                                      // (tc_conv2_kernel, CF_TC_CONV=2); 1 = three rounds (tc_conv_kernel, CF_TC_CONV=1)
     bool trace_done = false;
     int x_depth = 0;                  // x blocks prefetched into L2 ahead of the ring (CF_TC_XDEPTH); measured: no gain, extra DRAM reads
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
@@ -120,7 +121,7 @@ TcEngine* tc_create(const HostModel& hm) {
     e->simt = simt_create(hm);
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
     if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
-    if (const char* env = getenv("CF_TC_CONV")) e->conv_variant = atoi(env) == 1 ? 1 : 2;
+    if (const char* env = getenv("CF_TC_CONV")) e->conv_variant = std::min(4, std::max(1, atoi(env)));
     if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(0, atoi(env));
     if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
@@ -673,6 +674,532 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
+// ====================================================================== TK2 v3: the two residual blocks as two chains
+// Same mathematics, operand layouts and accumulator skew as tc_conv2_kernel (NRES == 2 only), but
+// the work of a position is split by residual block into two independently clocked chains so that
+// the MMA batch of one block runs on the tensor pipe while the other block's epilogue runs:
+//   chain X (block 0): batch o2[u-1], o3[u-2]                 -> epilogue writes o2, y0, o1[u+2]
+//   chain Y (block 1): batch [sc1|p1][u-3], p2[u-5], p3[u-6]  -> epilogue writes p1, p2, y1 (global)
+//   warps 0-7 / 8-15 : epilogue of X / Y, thread = (window, 16 of the 32 channels)
+//   warp 16 / 17     : MMA issuer of X / Y (warp-converged, elected lane)
+// The only coupling is y0 (output of block 0 = input of block 1).  It lives in TENSOR MEMORY as the
+// A operand of the [sc1|p1] MMAs (".ts" form: no shared-memory slice, no A-operand smem reads),
+// in a ring of 4 slots with full (X epilogue -> Y issuer) / empty (tcgen05.commit -> X epilogue)
+// barriers, so X may run up to three positions ahead of Y.
+// TMEM: o2 0, o3 32, p2 64, p3 96, [sc1|p1] ring of 4 at 128 + 64 k, y0 ring of 4 at 384 + 32 k
+// (per slot: hi K 0-15 | hi K 16-31 | lo K 0-15 | lo K 16-31, 8 columns each).
+constexpr uint32_t kConv3Smem = ConvParams::kBytes + 9 * kSliceBytes + 35 * 128 * 4 + 256;
+
+__global__ void __launch_bounds__(576, 1)
+tc_conv3_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
+                const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
+                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* prm = smem;
+    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 4 slices (o1 is produced two positions ahead)
+    uint8_t* o2 = o1 + 4 * kSliceBytes;
+    uint8_t* p1 = o2 + kSliceBytes;                   // ring of 3 slices
+    uint8_t* p2 = p1 + 3 * kSliceBytes;
+    float* xs = reinterpret_cast<float*>(p2 + kSliceBytes);      // [35][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 35 * 128);
+    uint64_t* bar_ready_x = &bars[0];
+    uint64_t* bar_mma_x = &bars[1];
+    uint64_t* bar_ready_y = &bars[2];
+    uint64_t* bar_mma_y = &bars[3];
+    uint64_t* bar_prm = &bars[4];
+    uint64_t* bar_y0_full = &bars[5];                 // [4]
+    uint64_t* bar_y0_empty = &bars[9];                // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    const float* fp = reinterpret_cast<const float*>(prm);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_ready_x, 8);
+        mbar_init(bar_mma_x, 1);
+        mbar_init(bar_ready_y, 8);
+        mbar_init(bar_mma_y, 1);
+        mbar_init(bar_prm, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_y0_full[i], 8); mbar_init(&bar_y0_empty[i], 1); }
+        fence_mbar_init();
+        mbar_expect_tx(bar_prm, ConvParams::kBytes);
+        bulk_g2s(prm, params, ConvParams::kBytes, bar_prm);
+    }
+    if (warp == 16) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    constexpr int kLastX = kWindow + 1;               // o3[34] at u = 36
+    constexpr int kFirstY = 3, kLastY = kWindow + 5;  // [sc1|p1][0] at u = 3, p3[34] at u = 40
+    constexpr uint32_t kTmY0 = 384;
+    mbar_wait(bar_prm, 0);
+
+    if (warp == 16) {
+        // ------------------------------------------------------------ issuer of chain X
+        const uint32_t elected = elect_one();
+        const uint32_t prm_u = smem_u32(prm), o1_u = smem_u32(o1), o2_u = smem_u32(o2);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int u = 0; u <= kLastX; ++u, ++it) {
+                mbar_wait(bar_ready_x, it & 1);
+                tc_fence_after_sync();
+                const int t1 = u - 1, t2 = u - 2;
+                if (t1 >= 0 && t1 < kWindow) {
+                    bool first = true;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = t1 + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma_pred<32>(tmem + 0, o1_u + (tt & 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
+                        first = false;
+                    }
+                }
+                if (t2 >= 0 && t2 < kWindow) conv_mma_pred<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
+                umma_commit_pred(bar_mma_x, elected);
+            }
+        }
+    } else if (warp == 17) {
+        // ------------------------------------------------------------ issuer of chain Y
+        const uint32_t elected = elect_one();
+        const uint32_t prm_u = smem_u32(prm), p1_u = smem_u32(p1), p2_u = smem_u32(p2);
+        constexpr uint32_t idesc64 = make_idesc_bf16(128, 64);
+        uint32_t it = 0, ny = 0;                       // ny: y0 positions consumed so far
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int u = kFirstY; u <= kLastY; ++u, ++it) {
+                mbar_wait(bar_ready_y, it & 1);
+                tc_fence_after_sync();
+                const int t3 = u - 3, t4 = u - 5, t5 = u - 6;
+                if (t3 < kWindow) {
+                    const uint32_t slot = ny & 3;
+                    mbar_wait(&bar_y0_full[slot], (ny >> 2) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t a = tmem + kTmY0 + slot * 32, d = tmem + 128 + (t3 & 3) * 64;
+                    const uint32_t w = prm_u + ConvParams::kW45;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t ap = a + (pass == 1 ? 16u : 0u);
+                        const uint32_t wp = w + (pass == 2 ? (uint32_t)(kC * 64 * 2) : 0u);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+                            umma_bf16_ts_pred(d, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc64,
+                                              !(pass == 0 && kk == 0), elected);
+                    }
+                    umma_commit_pred(&bar_y0_empty[slot], elected);
+                    ++ny;
+                }
+                if (t4 >= 0 && t4 < kWindow) {
+                    bool first = true;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = t4 + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma_pred<32>(tmem + 64, p1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
+                        first = false;
+                    }
+                }
+                if (t5 >= 0 && t5 < kWindow) conv_mma_pred<32>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
+                umma_commit_pred(bar_mma_y, elected);
+            }
+        }
+    } else {
+        const int ew = warp & 7;                      // warp within its epilogue group
+        const int q = ew & 3, ch = ew >> 2;
+        const int row = q * 32 + lane;
+        const int c0 = ch * 16;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + c0;
+        auto relu_bias = [&](uint32_t* r, int slot, float* v) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(fp + 32 * slot + c0 + i);
+                v[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
+                v[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
+                v[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
+                v[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+            }
+        };
+        if (warp < 8) {
+            // -------------------------------------------------------- epilogue of chain X
+            auto make_o1 = [&](int t) {               // o1[t] = relu(x a1 + b1) on CUDA cores
+                const float x = xs[t * 128 + row];
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
+                store_a_row16(o1 + (t & 3) * kSliceBytes, row, c0, v);
+            };
+            const uint32_t t_y0 = tmem + ((uint32_t)(q * 32) << 16) + kTmY0 + ch * 8;
+            uint32_t it = 0, ny = 0;                  // ny: y0 positions produced so far
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                // gather + normalise (infer.py:101-105, 32-38): the two threads of a window split its 35 samples
+                asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of xs are done
+                {
+                    const int64_t g = (tile0 + tile) * kTileWindows + row;
+                    const int nv = valid[g];
+                    const int64_t s0 = src[g];
+                    double shift = 0.0, scale = 1.0;
+                    if (raw && nv > 0) { const int r = read[g]; shift = stats[2 * r]; scale = stats[2 * r + 1]; }
+                    const int tb = ch ? 18 : 0, te = ch ? kWindow : 18;
+                    for (int t = tb; t < te; ++t) {
+                        float v = 0.f;
+                        if (t < nv) v = raw ? (float)(((double)raw[s0 + t] - shift) / scale) : xwin[s0 + t];
+                        xs[t * 128 + row] = v;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                make_o1(0);
+                make_o1(1);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready_x);
+                for (int u = 0; u <= kLastX; ++u, ++it) {
+                    const int t1 = u - 1, t2 = u - 2;
+                    const bool h1 = t1 >= 0 && t1 < kWindow, h2 = t2 >= 0 && t2 < kWindow;
+                    mbar_wait(bar_mma_x, it & 1);
+                    tc_fence_after_sync();
+                    uint32_t r1[16], r2[16];
+                    if (h1) tmem_ld16_nowait(t_lane + 0, r1);
+                    if (h2) tmem_ld16_nowait(t_lane + 32, r2);
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    float v[16];
+                    if (h1) { relu_bias(r1, 4, v); store_a_row16(o2, row, c0, v); }              // b2
+                    // o2 (and o1[u+1], made one iteration ago) are all the next X batch reads
+                    if (u < kLastX) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_ready_x);
+                    }
+                    if (h2) {
+                        relu_bias(r2, 5, v);                                                     // b3
+                        const float x = xs[t2 * 128 + row];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                        const uint32_t slot = ny & 3;
+                        if (ny >= 4) mbar_wait(&bar_y0_empty[slot], ((ny >> 2) - 1) & 1);
+                        tc_fence_after_sync();
+                        tmem_st8_u32(t_y0 + slot * 32, hi);
+                        tmem_st8_u32(t_y0 + slot * 32 + 16, lo);
+                        tmem_st_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_y0_full[slot]);
+                        ++ny;
+                    }
+                    if (u + 2 < kWindow) make_o1(u + 2);
+                }
+            }
+        } else {
+            // -------------------------------------------------------- epilogue of chain Y
+            uint32_t it = 0;
+            if (lane == 0) mbar_arrive(bar_ready_y);          // nothing to prepare for the first batch
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int u = kFirstY; u <= kLastY; ++u, ++it) {
+                    const int t3 = u - 3, t4 = u - 5, t5 = u - 6;
+                    const bool h3 = t3 < kWindow, h4 = t4 >= 0 && t4 < kWindow, h5 = t5 >= 0 && t5 < kWindow;
+                    mbar_wait(bar_mma_y, it & 1);
+                    tc_fence_after_sync();
+                    uint32_t r3[16], r4[16], r5[16], rs[16];
+                    if (h3) tmem_ld16_nowait(t_lane + 128 + (t3 & 3) * 64 + 32, r3);
+                    if (h4) tmem_ld16_nowait(t_lane + 64, r4);
+                    if (h5) {
+                        tmem_ld16_nowait(t_lane + 96, r5);
+                        tmem_ld16_nowait(t_lane + 128 + (t5 & 3) * 64, rs);
+                    }
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    float v[16];
+                    if (h3) { relu_bias(r3, 7, v); store_a_row16(p1 + (t3 % 3) * kSliceBytes, row, c0, v); }   // b5
+                    if (h4) { relu_bias(r4, 8, v); store_a_row16(p2, row, c0, v); }              // b6
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ready_y);
+                    if (h5) {
+                        relu_bias(r5, 9, v);                                                     // b7
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + (__uint_as_float(rs[i]) + fp[192 + c0 + i]), 0.f);   // + sc1 + b4
+                        store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc<512>(tmem);
+}
+
+// ====================================================================== TK2 v4: two chains, k = 3 operands in tensor memory
+// tc_conv3_kernel with the A operands of both k = 3 convolutions (the o1 and p1 rings) and y0 held in
+// TENSOR MEMORY: an N = 32 MMA that reads its 4 KB A operand from shared memory is bound by that
+// read (~38 cycles for 17 cycles of math); the ".ts" form only fetches the 1 KB weight slice.
+// To make room the [sc1|p1] accumulator is single-buffered: the epilogue thread that reads p1 also
+// takes its 16 channels of sc1 (+ b4) and parks them for three positions in a thread-private
+// shared-memory ring.  o2 and p2 (k = 1 operands, 6 MMAs each) stay in shared memory.
+// TMEM: o2 0, o3 32, p2 64, p3 96, [sc1|p1] 128 | y0 ring of 3 at 192 + 32 k | o1 ring of 4 at
+// 288 + 32 k | p1 ring of 3 at 416 + 32 k.  Operand slot: hi K 0-15 | hi K 16-31 | lo K 0-15 | lo K 16-31.
+constexpr uint32_t kConv4Smem = ConvParams::kBytes + 2 * kSliceBytes + 4 * (32 * 128 * 4) + 35 * 128 * 4 + 256;
+
+template <int N>
+__device__ __forceinline__ void conv_mma_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint32_t w_mat, bool first, uint32_t elected) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, N);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ap = tmem_a + (pass == 1 ? 16u : 0u);
+        const uint32_t wp = w_mat + (pass == 2 ? (uint32_t)(kC * N * 2) : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+            umma_bf16_ts_pred(tmem_d, ap + kk * 8, make_smem_desc(wp + kk * 2 * (N * 16), N * 16, 128), idesc,
+                              !(first && pass == 0 && kk == 0), elected);
+    }
+}
+
+// 16 channels of one window as split-bf16 A operand into a TMEM slot (this thread's K = 16 chunk)
+__device__ __forceinline__ void store_a_tmem16(uint32_t t_slot, const float* v) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    tmem_st8_u32(t_slot, hi);
+    tmem_st8_u32(t_slot + 16, lo);
+}
+
+__global__ void __launch_bounds__(576, 1)
+tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
+                const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
+                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* prm = smem;
+    uint8_t* o2 = smem + ConvParams::kBytes;
+    uint8_t* p2 = o2 + kSliceBytes;
+    float* sc_ring = reinterpret_cast<float*>(p2 + kSliceBytes);   // [4][32][128]
+    float* xs = sc_ring + 4 * 32 * 128;                             // [35][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 35 * 128);
+    uint64_t* bar_ready_x = &bars[0];
+    uint64_t* bar_mma_x = &bars[1];
+    uint64_t* bar_ready_y = &bars[2];
+    uint64_t* bar_mma_y = &bars[3];
+    uint64_t* bar_prm = &bars[4];
+    uint64_t* bar_y0_full = &bars[5];                 // [3]
+    uint64_t* bar_y0_empty = &bars[8];                // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    const float* fp = reinterpret_cast<const float*>(prm);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_ready_x, 8);
+        mbar_init(bar_mma_x, 1);
+        mbar_init(bar_ready_y, 8);
+        mbar_init(bar_mma_y, 1);
+        mbar_init(bar_prm, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(&bar_y0_full[i], 8); mbar_init(&bar_y0_empty[i], 1); }
+        fence_mbar_init();
+        mbar_expect_tx(bar_prm, ConvParams::kBytes);
+        bulk_g2s(prm, params, ConvParams::kBytes, bar_prm);
+    }
+    if (warp == 16) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    constexpr int kLastX = kWindow + 1;               // o3[34] at u = 36
+    constexpr int kFirstY = 3, kLastY = kWindow + 5;  // [sc1|p1][0] at u = 3, p3[34] at u = 40
+    constexpr uint32_t kTmScp1 = 128, kTmY0 = 192, kTmO1 = 288, kTmP1 = 416;
+    mbar_wait(bar_prm, 0);
+
+    if (warp == 16) {
+        // ------------------------------------------------------------ issuer of chain X
+        const uint32_t elected = elect_one();
+        const uint32_t prm_u = smem_u32(prm), o2_u = smem_u32(o2);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int u = 0; u <= kLastX; ++u, ++it) {
+                mbar_wait(bar_ready_x, it & 1);
+                tc_fence_after_sync();
+                const int t1 = u - 1, t2 = u - 2;
+                if (t1 >= 0 && t1 < kWindow) {
+                    bool first = true;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = t1 + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma_ts_pred<32>(tmem + 0, tmem + kTmO1 + (tt & 3) * 32, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
+                        first = false;
+                    }
+                }
+                if (t2 >= 0 && t2 < kWindow) conv_mma_pred<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
+                umma_commit_pred(bar_mma_x, elected);
+            }
+        }
+    } else if (warp == 17) {
+        // ------------------------------------------------------------ issuer of chain Y
+        const uint32_t elected = elect_one();
+        const uint32_t prm_u = smem_u32(prm), p2_u = smem_u32(p2);
+        uint32_t it = 0, ny = 0, ny_slot = 0, ny_par = 0;          // y0 positions consumed so far: slot = ny % 3
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int u = kFirstY; u <= kLastY; ++u, ++it) {
+                mbar_wait(bar_ready_y, it & 1);
+                tc_fence_after_sync();
+                const int t3 = u - 3, t4 = u - 5, t5 = u - 6;
+                if (t3 < kWindow) {
+                    mbar_wait(&bar_y0_full[ny_slot], ny_par);
+                    tc_fence_after_sync();
+                    conv_mma_ts_pred<64>(tmem + kTmScp1, tmem + kTmY0 + ny_slot * 32, prm_u + ConvParams::kW45, true, elected);
+                    umma_commit_pred(&bar_y0_empty[ny_slot], elected);
+                    ++ny;
+                    if (++ny_slot == 3) { ny_slot = 0; ny_par ^= 1; }
+                }
+                if (t4 >= 0 && t4 < kWindow) {
+                    bool first = true;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap) {
+                        const int tt = t4 + tap - 1;
+                        if (tt < 0 || tt >= kWindow) continue;
+                        conv_mma_ts_pred<32>(tmem + 64, tmem + kTmP1 + (tt % 3) * 32, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
+                        first = false;
+                    }
+                }
+                if (t5 >= 0 && t5 < kWindow) conv_mma_pred<32>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
+                umma_commit_pred(bar_mma_y, elected);
+            }
+        }
+    } else {
+        const int ew = warp & 7;                      // warp within its epilogue group
+        const int q = ew & 3, ch = ew >> 2;
+        const int row = q * 32 + lane;
+        const int c0 = ch * 16;
+        const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t t_lane = t_row + c0;           // this thread's 16 accumulator columns
+        const uint32_t t_opnd = t_row + ch * 8;       // this thread's K = 16 chunk of an operand slot
+        auto relu_bias = [&](uint32_t* r, int slot, float* v) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(fp + 32 * slot + c0 + i);
+                v[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
+                v[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
+                v[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
+                v[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+            }
+        };
+        if (warp < 8) {
+            // -------------------------------------------------------- epilogue of chain X
+            auto make_o1 = [&](int t) {               // o1[t] = relu(x a1 + b1) on CUDA cores
+                const float x = xs[t * 128 + row];
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
+                store_a_tmem16(t_opnd + kTmO1 + (t & 3) * 32, v);
+            };
+            uint32_t it = 0, ny = 0, ny_slot = 0, ny_par = 1;      // empty-barrier parity of the previous use
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                // gather + normalise (infer.py:101-105, 32-38): the two threads of a window split its 35 samples
+                asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of xs are done
+                {
+                    const int64_t g = (tile0 + tile) * kTileWindows + row;
+                    const int nv = valid[g];
+                    const int64_t s0 = src[g];
+                    double shift = 0.0, scale = 1.0;
+                    if (raw && nv > 0) { const int r = read[g]; shift = stats[2 * r]; scale = stats[2 * r + 1]; }
+                    const int tb = ch ? 18 : 0, te = ch ? kWindow : 18;
+                    for (int t = tb; t < te; ++t) {
+                        float v = 0.f;
+                        if (t < nv) v = raw ? (float)(((double)raw[s0 + t] - shift) / scale) : xwin[s0 + t];
+                        xs[t * 128 + row] = v;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // the previous tile's last X batch (which read o1 slots) completed before its last epilogue
+                make_o1(0);
+                make_o1(1);
+                tmem_st_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready_x);
+                for (int u = 0; u <= kLastX; ++u, ++it) {
+                    const int t1 = u - 1, t2 = u - 2;
+                    const bool h1 = t1 >= 0 && t1 < kWindow, h2 = t2 >= 0 && t2 < kWindow;
+                    mbar_wait(bar_mma_x, it & 1);
+                    tc_fence_after_sync();
+                    uint32_t r1[16], r2[16];
+                    if (h1) tmem_ld16_nowait(t_lane + 0, r1);
+                    if (h2) tmem_ld16_nowait(t_lane + 32, r2);
+                    tmem_ld_wait();
+                    float v[16];
+                    if (h1) { relu_bias(r1, 4, v); store_a_row16(o2, row, c0, v); }              // b2
+                    // o2 and o1[u+1] (made one iteration ago, in TMEM) are all the next X batch reads
+                    if (u < kLastX) {
+                        fence_proxy_async_smem();
+                        tmem_st_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_ready_x);
+                    }
+                    if (h2) {
+                        relu_bias(r2, 5, v);                                                     // b3
+                        const float x = xs[t2 * 128 + row];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
+                        if (ny >= 3) mbar_wait(&bar_y0_empty[ny_slot], ny_par);
+                        tc_fence_after_sync();
+                        store_a_tmem16(t_opnd + kTmY0 + ny_slot * 32, v);
+                        tmem_st_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_y0_full[ny_slot]);
+                        ++ny;
+                        if (++ny_slot == 3) { ny_slot = 0; ny_par ^= 1; }
+                    }
+                    if (u + 2 < kWindow) make_o1(u + 2);
+                }
+            }
+        } else {
+            // -------------------------------------------------------- epilogue of chain Y
+            float* sc_mine = sc_ring + c0 * 128 + row;            // + slot * 4096 + i * 128
+            uint32_t it = 0;
+            if (lane == 0) mbar_arrive(bar_ready_y);          // nothing to prepare for the first batch
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int u = kFirstY; u <= kLastY; ++u, ++it) {
+                    const int t3 = u - 3, t4 = u - 5, t5 = u - 6;
+                    const bool h3 = t3 < kWindow, h4 = t4 >= 0 && t4 < kWindow, h5 = t5 >= 0 && t5 < kWindow;
+                    mbar_wait(bar_mma_y, it & 1);
+                    tc_fence_after_sync();
+                    uint32_t r3[16], r4[16], r5[16], rs[16];
+                    if (h3) {
+                        tmem_ld16_nowait(t_lane + kTmScp1 + 32, r3);
+                        tmem_ld16_nowait(t_lane + kTmScp1, rs);
+                    }
+                    if (h4) tmem_ld16_nowait(t_lane + 64, r4);
+                    if (h5) tmem_ld16_nowait(t_lane + 96, r5);
+                    tmem_ld_wait();
+                    float v[16];
+                    if (h3) { relu_bias(r3, 7, v); store_a_tmem16(t_opnd + kTmP1 + (t3 % 3) * 32, v); }   // b5
+                    if (h4) { relu_bias(r4, 8, v); store_a_row16(p2, row, c0, v); }              // b6
+                    fence_proxy_async_smem();
+                    tmem_st_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ready_y);
+                    if (h3) {                                                                    // park sc1 + b4
+                        float* dst = sc_mine + (t3 & 3) * 4096;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[i * 128] = __uint_as_float(rs[i]) + fp[192 + c0 + i];
+                    }
+                    if (h5) {
+                        relu_bias(r5, 9, v);                                                     // b7
+                        const float* sc = sc_mine + (t5 & 3) * 4096;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + sc[i * 128], 0.f);     // + (sc1 + b4)
+                        store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
 // ====================================================================== TK3: input projection
@@ -1787,6 +2314,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3Smem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
@@ -1816,7 +2345,13 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         if (e->conv_params) {
             ProfScope ps(prof, KC_K2_CONV, stream);
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
-            if (e->conv_variant == 2) {
+            if (e->conv_variant == 4 && e->conv_nres == 2) {
+                tc_conv4_kernel<<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                  tab.read, tile0, (int)tiles, a0);
+            } else if (e->conv_variant >= 3 && e->conv_nres == 2) {
+                tc_conv3_kernel<<<grid, 576, kConv3Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                  tab.read, tile0, (int)tiles, a0);
+            } else if (e->conv_variant >= 2) {
                 if (e->conv_nres == 2)
                     tc_conv2_kernel<2><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                          tab.read, tile0, (int)tiles, a0);

@@ -128,11 +128,13 @@ def test_engine_cross_check_large():
         _check_intervals(a, sa, sb.astype(np.float64))
 
 
-@pytest.mark.parametrize("env", [{"CF_TC_FUSED": "1"}, {"CF_TC_UNFUSED": "1"}, {"CF_TC_CONV": "1"}],
-                         ids=["one-tile-fused", "unfused-pair", "three-round-conv"])
+@pytest.mark.parametrize("env", [{"CF_TC_FUSED": "1"}, {"CF_TC_UNFUSED": "1"}, {"CF_TC_CONV": "1"}, {"CF_TC_CONV": "2"},
+                                 {"CF_TC_CONV": "3"}],
+                         ids=["one-tile-fused", "unfused-pair", "three-round-conv", "one-round-conv", "two-chain-conv-smem"])
 def test_tcgen05_kernel_variants(env, monkeypatch):
-    """The alternative GRU kernels of the tcgen05 engine (one tile per CTA; projection + recurrence
-    as two kernels) stay parity-green: they are the cross-checks of the default two-tile kernel."""
+    """The alternative kernels of the tcgen05 engine (GRU: one tile per CTA; projection + recurrence
+    as two kernels.  Conv stack: three rounds per position; one round; two chains with operands in
+    shared memory) stay parity-green: they are the cross-checks of the default kernels."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     g = golden("forward_resnetrnn_shipped.npz")

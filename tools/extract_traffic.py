@@ -13,7 +13,8 @@ import subprocess
 import sys
 
 CLASSES = {"tc_gru_fused2_kernel": "k4_gru_recurrence", "tc_gru_fused_kernel": "k4_gru_recurrence",
-           "tc_conv2_kernel": "k2_conv_stack", "tc_conv_kernel": "k2_conv_stack"}
+           "tc_conv4_kernel": "k2_conv_stack", "tc_conv3_kernel": "k2_conv_stack", "tc_conv2_kernel": "k2_conv_stack",
+           "tc_conv_kernel": "k2_conv_stack"}
 UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 if __name__ == "__main__":

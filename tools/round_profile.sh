@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-end measurement set (run under gpurun on one B200): GPU tests, the bench line, the ncu launch
+# list of a shortened bench, and one --set full capture of the conv stack + the three GRU-layer launches.
+set -u
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_gpu.txt
+cat gpurun_out/pytest_gpu.txt
+timeout 900 python bench.py --steps 10 --warmup 3 --cpu-reads 400 > gpurun_out/bench_full.txt 2> gpurun_out/bench_full.err
+tail -c 600 gpurun_out/bench_full.txt
+timeout 600 python bench.py --steps 2 --warmup 3 --reads-per-step 128 --no-cpu-baseline > gpurun_out/bench_short.txt 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 300 --csv --log-file gpurun_out/ncu_launches.csv \
+    python bench.py --steps 2 --warmup 3 --reads-per-step 128 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+timeout 300 python tools/profile_workload.py 96 2 > gpurun_out/prof_workload.txt 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_gru_fused2|tc_conv4' -s 4 -c 4 -f -o gpurun_out/prof_main \
+    python tools/profile_workload.py 96 2 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
