@@ -543,6 +543,13 @@ int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int3
     return cf::tc_selftest_xproj(a_dev, n_blocks, k, wx_host, bias_host, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int cf_selftest_f16e5(int32_t device, const float* a_dev, int32_t k, int32_t n, const float* w_host, int32_t mode,
+                      float* out_dev, void* stream) {
+    if (!a_dev || !w_host || !out_dev) { cf::set_error("cf_selftest_f16e5: bad argument"); return CF_ERR_BAD_ARG; }
+    CF_TRY(cf::use_device(device));
+    return cf::tc_selftest_f16e5(a_dev, k, n, w_host, mode, out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int64_t cf_launch_count(void) { return (int64_t)cf::g_launches.load(); }
 
 int cf_model_num_tensors(const cf_model_desc* desc) {

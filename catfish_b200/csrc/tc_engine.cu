@@ -36,6 +36,8 @@ constexpr int kTcChunkTiles = 1184;  // tiles per internal pass (8 tiles per cha
 constexpr float kGateScale = -1.4426950408889634f;    // -log2(e)
 constexpr float kCandScale = 2.8853900817779268f;     // 2 log2(e)
 
+constexpr int kFmtBf16x3 = 0, kFmtF16E5 = 1;   // operand formats, see "operand formats" below
+
 struct ConvParams {                    // byte offsets inside the parameter block
     static constexpr int kFloats = 10 * 32;              // a_sc b_sc a1 b1 | b2 b3 b4 b5 b6 b7
     static constexpr int kW2 = kFloats * 4;              // 3 taps x {hi, lo} x [4][32][8]
@@ -63,6 +65,29 @@ static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std:
             const size_t idx = ((size_t)(k / 8) * N + n) * 8 + (k % 8);
             hi[idx] = h;
             lo[idx] = l;
+        }
+}
+
+// B operand in the "f16e5" format (tc_ptx.cuh): plane 0 = fp16 [K/8][N][8]; plane 1 = e5m2
+// [2K/16][N][16]: per chunk of 16 K-rows first the 16 fp16 parts / S, then the 16 remainders * S -
+// the K' order the A-side producers use.  Same byte count and the same per-chunk descriptor offsets
+// as the split-bf16 layout.
+static void pack_b_operand_f16e5(const float* w, int K, int N, int ldw, int col0, std::vector<__nv_bfloat16>* out,
+                                 float scale = 1.f, int n_split = 1 << 30, float scale_hi = 1.f) {
+    const size_t plane = (size_t)K * N;
+    const size_t base = out->size();
+    out->resize(base + 2 * plane);
+    uint16_t* main = reinterpret_cast<uint16_t*>(out->data() + base);
+    uint8_t* corr = reinterpret_cast<uint8_t*>(out->data() + base + plane);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float v = w[(size_t)k * ldw + col0 + n] * (n < n_split ? scale : scale_hi);
+            const __half h = __float2half_rn(v);
+            const float hf = __half2float(h);
+            main[((size_t)(k / 8) * N + n) * 8 + (k % 8)] = *reinterpret_cast<const uint16_t*>(&h);
+            const int c = k / 16, kc = k % 16;
+            corr[((size_t)(2 * c) * N + n) * 16 + kc] = (uint8_t)__nv_cvt_float_to_fp8(hf / kCorrScale, __NV_SATFINITE, __NV_E5M2);
+            corr[((size_t)(2 * c + 1) * N + n) * 16 + kc] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * kCorrScale, __NV_SATFINITE, __NV_E5M2);
         }
 }
 
@@ -94,6 +119,8 @@ struct TcEngine {
     int x_depth = 0;                  // x blocks prefetched into L2 ahead of the ring (CF_TC_XDEPTH); measured: no gain, extra DRAM reads
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
+    int fmt = kFmtBf16x3;             // operand format of the default kernels (kFmtF16E5 unless CF_TC_FMT=0 or a cross-check
+                                      // variant / a network the default kernels do not cover is selected)
 };
 
 bool tc_supported(const HostModel& hm) {
@@ -124,6 +151,14 @@ TcEngine* tc_create(const HostModel& hm) {
     if (const char* env = getenv("CF_TC_CONV")) e->conv_variant = std::min(4, std::max(1, atoi(env)));
     if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(0, atoi(env));
     if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
+    {
+        // fp16 + e5m2 operands need every tensor-core kernel of the pass to speak the format: the default
+        // conv stack (two residual blocks) followed by fused GRU layers only
+        const bool covered = hm.desc.network_type == CF_NET_RESNET_RNN && hm.n_res() == 2 && hm.conv_channels() == kC &&
+                             e->conv_variant == 4 && e->fused_variant == 2 && e->use_fused;
+        const char* env = getenv("CF_TC_FMT");
+        e->fmt = covered && !(env && env[0] == '0') ? kFmtF16E5 : kFmtBf16x3;
+    }
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
         std::vector<uint8_t> blk(ConvParams::kBytes, 0);
@@ -132,7 +167,7 @@ TcEngine* tc_create(const HostModel& hm) {
         put(0, hm.convs[0].w); put(1, hm.convs[0].b);          // shortcut of block 0: [1][1][32]
         put(2, hm.convs[1].w); put(3, hm.convs[1].b);
         put(4, hm.convs[2].b); put(5, hm.convs[3].b);
-        auto put_w = [&](int off, const float* w, int n, int ldw, int col0, int dst_col0, int n_total) {
+        auto put_w_bf16 = [&](int off, const float* w, int n, int ldw, int col0, int dst_col0, int n_total) {
             // pack a [32][n] matrix into columns [dst_col0, dst_col0 + n) of a {hi, lo} x [4][n_total][8] operand
             __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(blk.data() + off);
             __nv_bfloat16* lo = hi + 32 * n_total;
@@ -144,6 +179,26 @@ TcEngine* tc_create(const HostModel& hm) {
                     hi[idx] = h;
                     lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
                 }
+        };
+        auto& put_w_bf = put_w_bf16;
+        auto put_w_e5 = [&](int off, const float* w, int n, int ldw, int col0, int dst_col0, int n_total) {
+            // the same [32][n] matrix in the f16e5 format: fp16 plane, then e5m2 [4][n_total][16]
+            uint16_t* mn = reinterpret_cast<uint16_t*>(blk.data() + off);
+            uint8_t* cr = blk.data() + off + 32 * n_total * 2;
+            for (int k = 0; k < 32; ++k)
+                for (int j = 0; j < n; ++j) {
+                    const float v = w[(size_t)k * ldw + col0 + j];
+                    const __half h = __float2half_rn(v);
+                    const float hf = __half2float(h);
+                    mn[((size_t)(k / 8) * n_total + dst_col0 + j) * 8 + (k % 8)] = *reinterpret_cast<const uint16_t*>(&h);
+                    const int c = k / 16, kc = k % 16;
+                    cr[((size_t)(2 * c) * n_total + dst_col0 + j) * 16 + kc] = (uint8_t)__nv_cvt_float_to_fp8(hf / kCorrScale, __NV_SATFINITE, __NV_E5M2);
+                    cr[((size_t)(2 * c + 1) * n_total + dst_col0 + j) * 16 + kc] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * kCorrScale, __NV_SATFINITE, __NV_E5M2);
+                }
+        };
+        auto put_w = [&](int off, const float* w, int n, int ldw, int col0, int dst_col0, int n_total) {
+            if (e->fmt == kFmtF16E5) put_w_e5(off, w, n, ldw, col0, dst_col0, n_total);
+            else put_w_bf(off, w, n, ldw, col0, dst_col0, n_total);
         };
         for (int tap = 0; tap < 3; ++tap) put_w(ConvParams::kW2 + tap * 4096, hm.convs[2].w.data() + tap * 32 * 32, 32, 32, 0, 0, 32);
         put_w(ConvParams::kW3, hm.convs[3].w.data(), 32, 32, 0, 0, 32);
@@ -192,9 +247,10 @@ TcEngine* tc_create(const HostModel& hm) {
                 const GruDir& g = hm.gru[2 * l + d];
                 // exponent domain: gates scaled by -log2(e), candidate by 2 log2(e) (see sigmoid4_z / tanh4_z)
                 // x rows of gates/kernel and candidate/kernel side by side: one N = 192 operand
-                pack_b_operand(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
-                pack_b_operand(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale);
-                pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale);
+                auto pack = e->fmt == kFmtF16E5 ? pack_b_operand_f16e5 : pack_b_operand;
+                pack(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
+                pack(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale, 1 << 30, 1.f);
+                pack(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale, 1 << 30, 1.f);
             }
             L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, wf));
             std::vector<float> bz(2 * kNX);
@@ -932,6 +988,67 @@ tc_conv3_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
     if (warp == 16) tmem_dealloc<512>(tmem);
 }
 
+// ====================================================================== operand formats
+// FMT 0 = split bf16, three MMAs per K = 16 chunk (bf16x3).  FMT 1 = fp16 + e5m2 corrections, two
+// MMAs per chunk ("f16e5", tc_ptx.cuh).  Both use the same byte positions everywhere: plane 0 holds
+// the 16-bit main operand, plane 1 (same size) the bf16 remainders or, per chunk of 16 K values,
+// 16 remainder bytes followed by 16 down-scaled main bytes.
+
+// Four consecutive values i..i+3 (i = 0, 4, 8, 12 inside a 16-value chunk) into the chunk's 8 main
+// words and 8 second-plane words.
+template <int FMT>
+__device__ __forceinline__ void split4(float v0, float v1, float v2, float v3, int i, uint32_t* m8, uint32_t* s8) {
+    if (FMT == kFmtBf16x3) {
+        split_bf16x2(v0, v1, m8[i >> 1], s8[i >> 1]);
+        split_bf16x2(v2, v3, m8[(i >> 1) + 1], s8[(i >> 1) + 1]);
+    } else {
+        uint32_t la, ha, lb, hb;
+        split_f16e5x2(v0, v1, m8[i >> 1], la, ha);
+        split_f16e5x2(v2, v3, m8[(i >> 1) + 1], lb, hb);
+        s8[i >> 2] = la | (lb << 16);
+        s8[4 + (i >> 2)] = ha | (hb << 16);
+    }
+}
+
+// 16 channels of one window into an operand slice {plane 0, plane 1} x [4][128][8 x 16 bit] in shared
+// or global memory / into a K = 16 chunk of a TMEM operand slot (plane 1 sixteen columns further).
+template <int FMT>
+__device__ __forceinline__ void store_a_row16_f(uint8_t* slice, int row, int c0, const float* v) {
+    uint32_t m8[8], s8[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) split4<FMT>(v[i], v[i + 1], v[i + 2], v[i + 3], i, m8, s8);
+    uint8_t* dst = slice + (c0 / 8) * 2048 + row * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(m8[0], m8[1], m8[2], m8[3]);
+    *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(m8[4], m8[5], m8[6], m8[7]);
+    *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(s8[0], s8[1], s8[2], s8[3]);
+    *reinterpret_cast<uint4*>(dst + 8192 + 2048) = make_uint4(s8[4], s8[5], s8[6], s8[7]);
+}
+template <int FMT>
+__device__ __forceinline__ void store_a_tmem16_f(uint32_t t_slot, const float* v) {
+    uint32_t m8[8], s8[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) split4<FMT>(v[i], v[i + 1], v[i + 2], v[i + 3], i, m8, s8);
+    tmem_st8_u32(t_slot, m8);
+    tmem_st8_u32(t_slot + 16, s8);
+}
+
+// All MMAs of one K = 32 operand slice against one [32 x N] weight matrix ({plane 0, plane 1}).
+template <int N, int FMT>
+__device__ __forceinline__ void conv_mma_f(uint32_t tmem_d, uint32_t a_slice, uint32_t w_mat, bool first, uint32_t elected) {
+    if (FMT == kFmtBf16x3) {
+        conv_mma_pred<N>(tmem_d, a_slice, w_mat, first, elected);
+    } else {
+        constexpr uint32_t id16 = make_idesc_f16(128, N), id8 = make_idesc_e5m2(128, N);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            umma_bf16_pred(tmem_d, make_smem_desc(a_slice + kk * 4096, 2048, 128),
+                           make_smem_desc(w_mat + kk * 2 * (N * 16), N * 16, 128), id16, !(first && kk == 0), elected);
+            umma_f8_pred(tmem_d, make_smem_desc(a_slice + 8192 + kk * 4096, 2048, 128),
+                         make_smem_desc(w_mat + kC * N * 2 + kk * 2 * (N * 16), N * 16, 128), id8, 1, elected);
+        }
+    }
+}
+
 // ====================================================================== TK2 v4: two chains, k = 3 operands in tensor memory
 // tc_conv3_kernel with the A operands of both k = 3 convolutions (the o1 and p1 rings) and y0 held in
 // TENSOR MEMORY: an N = 32 MMA that reads its 4 KB A operand from shared memory is bound by that
@@ -943,8 +1060,19 @@ tc_conv3_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
 // 288 + 32 k | p1 ring of 3 at 416 + 32 k.  Operand slot: hi K 0-15 | hi K 16-31 | lo K 0-15 | lo K 16-31.
 constexpr uint32_t kConv4Smem = ConvParams::kBytes + 2 * kSliceBytes + 4 * (32 * 128 * 4) + 35 * 128 * 4 + 256;
 
-template <int N>
+template <int N, int FMT>
 __device__ __forceinline__ void conv_mma_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint32_t w_mat, bool first, uint32_t elected) {
+    if (FMT == kFmtF16E5) {
+        constexpr uint32_t id16 = make_idesc_f16(128, N), id8 = make_idesc_e5m2(128, N);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            umma_bf16_ts_pred(tmem_d, tmem_a + kk * 8, make_smem_desc(w_mat + kk * 2 * (N * 16), N * 16, 128), id16,
+                              !(first && kk == 0), elected);
+            umma_f8_ts_pred(tmem_d, tmem_a + 16 + kk * 8, make_smem_desc(w_mat + kC * N * 2 + kk * 2 * (N * 16), N * 16, 128),
+                            id8, 1, elected);
+        }
+        return;
+    }
     constexpr uint32_t idesc = make_idesc_bf16(128, N);
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
@@ -957,15 +1085,7 @@ __device__ __forceinline__ void conv_mma_ts_pred(uint32_t tmem_d, uint32_t tmem_
     }
 }
 
-// 16 channels of one window as split-bf16 A operand into a TMEM slot (this thread's K = 16 chunk)
-__device__ __forceinline__ void store_a_tmem16(uint32_t t_slot, const float* v) {
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    tmem_st8_u32(t_slot, hi);
-    tmem_st8_u32(t_slot + 16, lo);
-}
-
+template <int FMT>
 __global__ void __launch_bounds__(576, 1)
 tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
                 const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
@@ -1025,11 +1145,11 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     for (int tap = 0; tap < 3; ++tap) {
                         const int tt = t1 + tap - 1;
                         if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_ts_pred<32>(tmem + 0, tmem + kTmO1 + (tt & 3) * 32, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
+                        conv_mma_ts_pred<32, FMT>(tmem + 0, tmem + kTmO1 + (tt & 3) * 32, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
                         first = false;
                     }
                 }
-                if (t2 >= 0 && t2 < kWindow) conv_mma_pred<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
+                if (t2 >= 0 && t2 < kWindow) conv_mma_f<32, FMT>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
                 umma_commit_pred(bar_mma_x, elected);
             }
         }
@@ -1046,7 +1166,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 if (t3 < kWindow) {
                     mbar_wait(&bar_y0_full[ny_slot], ny_par);
                     tc_fence_after_sync();
-                    conv_mma_ts_pred<64>(tmem + kTmScp1, tmem + kTmY0 + ny_slot * 32, prm_u + ConvParams::kW45, true, elected);
+                    conv_mma_ts_pred<64, FMT>(tmem + kTmScp1, tmem + kTmY0 + ny_slot * 32, prm_u + ConvParams::kW45, true, elected);
                     umma_commit_pred(&bar_y0_empty[ny_slot], elected);
                     ++ny;
                     if (++ny_slot == 3) { ny_slot = 0; ny_par ^= 1; }
@@ -1057,11 +1177,11 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     for (int tap = 0; tap < 3; ++tap) {
                         const int tt = t4 + tap - 1;
                         if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_ts_pred<32>(tmem + 64, tmem + kTmP1 + (tt % 3) * 32, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
+                        conv_mma_ts_pred<32, FMT>(tmem + 64, tmem + kTmP1 + (tt % 3) * 32, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
                         first = false;
                     }
                 }
-                if (t5 >= 0 && t5 < kWindow) conv_mma_pred<32>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
+                if (t5 >= 0 && t5 < kWindow) conv_mma_f<32, FMT>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
                 umma_commit_pred(bar_mma_y, elected);
             }
         }
@@ -1090,7 +1210,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
-                store_a_tmem16(t_opnd + kTmO1 + (t & 3) * 32, v);
+                store_a_tmem16_f<FMT>(t_opnd + kTmO1 + (t & 3) * 32, v);
             };
             uint32_t it = 0, ny = 0, ny_slot = 0, ny_par = 1;      // empty-barrier parity of the previous use
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1127,7 +1247,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     if (h2) tmem_ld16_nowait(t_lane + 32, r2);
                     tmem_ld_wait();
                     float v[16];
-                    if (h1) { relu_bias(r1, 4, v); store_a_row16(o2, row, c0, v); }              // b2
+                    if (h1) { relu_bias(r1, 4, v); store_a_row16_f<FMT>(o2, row, c0, v); }              // b2
                     // o2 and o1[u+1] (made one iteration ago, in TMEM) are all the next X batch reads
                     if (u < kLastX) {
                         fence_proxy_async_smem();
@@ -1143,7 +1263,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
                         if (ny >= 3) mbar_wait(&bar_y0_empty[ny_slot], ny_par);
                         tc_fence_after_sync();
-                        store_a_tmem16(t_opnd + kTmY0 + ny_slot * 32, v);
+                        store_a_tmem16_f<FMT>(t_opnd + kTmY0 + ny_slot * 32, v);
                         tmem_st_wait();
                         tc_fence_before_sync();
                         __syncwarp();
@@ -1174,8 +1294,8 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     if (h5) tmem_ld16_nowait(t_lane + 96, r5);
                     tmem_ld_wait();
                     float v[16];
-                    if (h3) { relu_bias(r3, 7, v); store_a_tmem16(t_opnd + kTmP1 + (t3 % 3) * 32, v); }   // b5
-                    if (h4) { relu_bias(r4, 8, v); store_a_row16(p2, row, c0, v); }              // b6
+                    if (h3) { relu_bias(r3, 7, v); store_a_tmem16_f<FMT>(t_opnd + kTmP1 + (t3 % 3) * 32, v); }   // b5
+                    if (h4) { relu_bias(r4, 8, v); store_a_row16_f<FMT>(p2, row, c0, v); }              // b6
                     fence_proxy_async_smem();
                     tmem_st_wait();
                     tc_fence_before_sync();
@@ -1191,7 +1311,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                         const float* sc = sc_mine + (t5 & 3) * 4096;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + sc[i * 128], 0.f);     // + (sc1 + b4)
-                        store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
+                        store_a_row16_f<FMT>(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
                     }
                 }
             }
@@ -1900,7 +2020,7 @@ template <int KX> struct GruF2Cfg {
     static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarFull = 5, kBarEmpty = 5 + kStages;
 };
 
-template <int KX>
+template <int KX, int FMT>
 __global__ void __launch_bounds__(608, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
@@ -2000,9 +2120,12 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         // Warp-converged: all lanes run the control flow and the waits, one elected lane issues
         // (descriptor arithmetic stays on the uniform datapath: ~10 instead of ~80 cycles per MMA).
         {
-            constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
-            constexpr uint32_t idesc_c = make_idesc_bf16(128, kH);
-            constexpr uint32_t idesc_x = make_idesc_bf16(128, kNX);
+            constexpr bool kE5 = FMT == kFmtF16E5;        // plane 1 = e5m2 corrections (one kind::f8f6f4 MMA per chunk)
+            constexpr uint32_t idesc_g = kE5 ? make_idesc_f16(128, 2 * kH) : make_idesc_bf16(128, 2 * kH);
+            constexpr uint32_t idesc_c = kE5 ? make_idesc_f16(128, kH) : make_idesc_bf16(128, kH);
+            constexpr uint32_t idesc_x = kE5 ? make_idesc_f16(128, kNX) : make_idesc_bf16(128, kNX);
+            constexpr uint32_t idesc_g8 = make_idesc_e5m2(128, 2 * kH), idesc_c8 = make_idesc_e5m2(128, kH);
+            constexpr uint32_t idesc_x8 = make_idesc_e5m2(128, kNX);
             const uint32_t elected = elect_one();
             const int c = warp - 16;
             const uint32_t s0 = smem_u32(smem);
@@ -2021,11 +2144,18 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     mbar_wait(&b[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
                     tc_fence_after_sync();
                     const uint32_t a0 = s0 + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
+                    if (kE5) {
+                        const uint32_t wx = s0 + Cfg::kWx + kk * 2 * (kNX * 16);
+                        umma_bf16_pred(dg, make_smem_desc(a0, 2048, 128), make_smem_desc(wx, kNX * 16, 128), idesc_x, kk != 0, elected);
+                        umma_f8_pred(dg, make_smem_desc(a0 + 4096u, 2048, 128),
+                                     make_smem_desc(wx + (uint32_t)KX * kNX * 2, kNX * 16, 128), idesc_x8, 1, elected);
+                    } else {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
-                        const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
-                        umma_bf16_pred(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0, elected);
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
+                            const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
+                            umma_bf16_pred(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0, elected);
+                        }
                     }
                     umma_commit_pred(&b[Cfg::kBarEmpty + st], elected);
                     if (lane == 0) CF_TR(c, gs, 20 + kk);
@@ -2034,13 +2164,22 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 mbar_wait(&b[Cfg::kBarH], par);
                 if (lane == 0) CF_TR(c, gs, 30);
                 tc_fence_after_sync();
+                if (kE5) {
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
-                    const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
+                    for (int kk = 0; kk < kH / 16; ++kk) {
+                        const uint32_t wp = s0 + Cfg::kWgh + kk * 2 * (128 * 16);
+                        umma_bf16_ts_pred(dg, ta + kk * 8, make_smem_desc(wp, 128 * 16, 128), idesc_g, 1, elected);
+                        umma_f8_ts_pred(dg, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 128 * 2, 128 * 16, 128), idesc_g8, 1, elected);
+                    }
+                } else {
 #pragma unroll
-                    for (int kk = 0; kk < kH / 16; ++kk)
-                        umma_bf16_ts_pred(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1, elected);
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
+                        const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
+#pragma unroll
+                        for (int kk = 0; kk < kH / 16; ++kk)
+                            umma_bf16_ts_pred(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1, elected);
+                    }
                 }
                 umma_commit_pred(&b[Cfg::kBarG], elected);
                 if (lane == 0) CF_TR(c, gs, 31);
@@ -2048,13 +2187,22 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 mbar_wait(&b[Cfg::kBarRh], par);
                 if (lane == 0) CF_TR(c, gs, 40);
                 tc_fence_after_sync();
+                if (kE5) {
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
-                    const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
+                    for (int kk = 0; kk < kH / 16; ++kk) {
+                        const uint32_t wp = s0 + Cfg::kWch + kk * 2 * (64 * 16);
+                        umma_bf16_ts_pred(dc, ta + kk * 8, make_smem_desc(wp, 64 * 16, 128), idesc_c, 1, elected);
+                        umma_f8_ts_pred(dc, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 64 * 2, 64 * 16, 128), idesc_c8, 1, elected);
+                    }
+                } else {
 #pragma unroll
-                    for (int kk = 0; kk < kH / 16; ++kk)
-                        umma_bf16_ts_pred(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1, elected);
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
+                        const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
+#pragma unroll
+                        for (int kk = 0; kk < kH / 16; ++kk)
+                            umma_bf16_ts_pred(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1, elected);
+                    }
                 }
                 umma_commit_pred(&b[Cfg::kBarC], elected);
                 if (lane == 0) CF_TR(c, gs, 41);
@@ -2116,8 +2264,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                             z[2] = __uint_as_float(ar[c0 + i + 2]) + b4.z; z[3] = __uint_as_float(ar[c0 + i + 3]) + b4.w;
                             sigmoid4_z(z, r);
 #endif
-                            split_bf16x2(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], hi[i >> 1], lo[i >> 1]);
-                            split_bf16x2(r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                            split4<FMT>(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], i, hi, lo);
                         }
                         tmem_st8_u32(t_ahi + c0 / 2, hi);
                         tmem_st8_u32(t_alo + c0 / 2, lo);
@@ -2177,8 +2324,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
-                    split_bf16x2(h[i], h[i + 1], hi[i >> 1], lo[i >> 1]);
-                    split_bf16x2(h[i + 2], h[i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                    split4<FMT>(h[i], h[i + 1], h[i + 2], h[i + 3], i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
                 }
                 tmem_st8_u32(t_ahi, hi);
                 tmem_st8_u32(t_ahi + 8, hi + 8);
@@ -2310,12 +2456,15 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<128>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3Smem));
-        CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
+        CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
@@ -2346,8 +2495,12 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             ProfScope ps(prof, KC_K2_CONV, stream);
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
             if (e->conv_variant == 4 && e->conv_nres == 2) {
-                tc_conv4_kernel<<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                  tab.read, tile0, (int)tiles, a0);
+                if (e->fmt == kFmtF16E5)
+                    tc_conv4_kernel<1><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                         tab.read, tile0, (int)tiles, a0);
+                else
+                    tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                         tab.read, tile0, (int)tiles, a0);
             } else if (e->conv_variant >= 3 && e->conv_nres == 2) {
                 tc_conv3_kernel<<<grid, 576, kConv3Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                   tab.read, tile0, (int)tiles, a0);
@@ -2391,13 +2544,20 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                         CF_CUDA(cudaMemsetAsync(trace_dev, 0, 5 * 200 * 2 * sizeof(long long), stream));
                     }
                     const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
-                    if (L.in == kC)
-                        tc_gru_fused2_kernel<32><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth, nullptr);
+                    const float* hw_l = last ? e->head_w : nullptr;
+                    float* hp_l = last ? head_part : nullptr;
+                    if (L.in == kC && e->fmt == kFmtF16E5)
+                        tc_gru_fused2_kernel<32, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
+                    else if (L.in == kC)
+                        tc_gru_fused2_kernel<32, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
+                    else if (e->fmt == kFmtF16E5)
+                        tc_gru_fused2_kernel<128, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
                     else
-                        tc_gru_fused2_kernel<128><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->x_depth,
-                            trace_dev);
+                        tc_gru_fused2_kernel<128, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
                     CF_LAUNCHED();
                     if (trace_dev) {
                         // debug: dump the timeline of block 0 and stop tracing
@@ -2511,6 +2671,100 @@ int tc_selftest_xproj(const float* a_dev, int64_t n_blocks, int K, const float* 
     CF_LAUNCHED();
     CF_CUDA(cudaStreamSynchronize(stream));
     w.release(); b.release(); a.release();
+    return CF_OK;
+}
+
+// ====================================================================== self-test of the f16e5 MMA pair
+// out[w][n] = sum_k a[w][k] wm[k][n] for one 128-row tile through the fp16 + e5m2-correction scheme:
+// A produced on the device by split_f16e5_chunk into shared memory (mode 0, ".ss") or tensor memory
+// (mode 1, ".ts"), B packed on the host by pack_b_operand_f16e5.  Pins the operand byte orders, the
+// kind::f8f6f4 descriptors and the mixing of MMA kinds on one fp32 accumulator.
+__global__ void __launch_bounds__(128, 1)
+tc_selftest_f16e5_kernel(const float* __restrict__ a, const uint8_t* __restrict__ wpk, int K, int N, int mode,
+                         float* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* a_s = smem;                               // {fp16 [K/8][128][8] | e5m2 [2K/16][128][16]}
+    uint8_t* w_s = smem + 128 * K * 4;                 // {fp16 [K/8][N][8] | e5m2 [2K/16][N][16]}
+    uint64_t* bar = reinterpret_cast<uint64_t*>(w_s + (size_t)N * K * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int row = threadIdx.x, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    for (int i = threadIdx.x; i < N * K * 4 / 16; i += 128)
+        reinterpret_cast<uint4*>(w_s)[i] = reinterpret_cast<const uint4*>(wpk)[i];
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t kTmA = 128;                      // operand columns: chunk c -> fp16 at 16 c, e5m2 at 16 c + 8
+    for (int c = 0; c < K / 16; ++c) {
+        float v[16];
+        for (int i = 0; i < 16; ++i) v[i] = a[(size_t)row * K + 16 * c + i];
+        uint32_t m8[8], lo4[4], hi4[4];
+        split_f16e5_chunk(v, m8, lo4, hi4);
+        if (mode == 0) {
+            *reinterpret_cast<uint4*>(a_s + (2 * c) * 2048 + row * 16) = make_uint4(m8[0], m8[1], m8[2], m8[3]);
+            *reinterpret_cast<uint4*>(a_s + (2 * c + 1) * 2048 + row * 16) = make_uint4(m8[4], m8[5], m8[6], m8[7]);
+            uint8_t* corr = a_s + 128 * K * 2;
+            *reinterpret_cast<uint4*>(corr + (2 * c) * 2048 + row * 16) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            *reinterpret_cast<uint4*>(corr + (2 * c + 1) * 2048 + row * 16) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+        } else {
+            uint32_t c8[8] = {lo4[0], lo4[1], lo4[2], lo4[3], hi4[0], hi4[1], hi4[2], hi4[3]};
+            tmem_st8_u32(t_row + kTmA + 16 * c, m8);
+            tmem_st8_u32(t_row + kTmA + 16 * c + 8, c8);
+        }
+    }
+    fence_proxy_async_smem();
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after_sync();
+        const uint32_t elected = elect_one();
+        const uint32_t a_u = smem_u32(a_s), w_u = smem_u32(w_s);
+        const uint32_t id16 = make_idesc_f16(128, N), id8 = make_idesc_e5m2(128, N);
+        for (int c = 0; c < K / 16; ++c) {
+            const uint64_t bm = make_smem_desc(w_u + c * 2 * (N * 16), N * 16, 128);
+            const uint64_t bc = make_smem_desc(w_u + K * N * 2 + c * 2 * (N * 16), N * 16, 128);
+            if (mode == 0) {
+                umma_bf16_pred(tmem, make_smem_desc(a_u + c * 4096, 2048, 128), bm, id16, c > 0, elected);
+                umma_f8_pred(tmem, make_smem_desc(a_u + 128 * K * 2 + c * 4096, 2048, 128), bc, id8, 1, elected);
+            } else {
+                umma_bf16_ts_pred(tmem, tmem + kTmA + 16 * c, bm, id16, c > 0, elected);
+                umma_f8_ts_pred(tmem, tmem + kTmA + 16 * c + 8, bc, id8, 1, elected);
+            }
+        }
+        umma_commit_pred(bar, elected);
+    }
+    mbar_wait(bar, 0);
+    tc_fence_after_sync();
+    for (int n0 = 0; n0 < N; n0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + n0, v);
+        for (int i = 0; i < 16; ++i) out[(size_t)row * N + n0 + i] = v[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+int tc_selftest_f16e5(const float* a_dev, int K, int N, const float* w_host, int mode, float* out_dev, cudaStream_t stream) {
+    if (K % 16 || K < 16 || K > 64 || N % 16 || N < 16 || N > 128 || (mode != 0 && mode != 1)) {
+        set_error("selftest_f16e5: K in {16..64} and N in {16..128}, multiples of 16; mode 0 or 1");
+        return CF_ERR_BAD_ARG;
+    }
+    std::vector<__nv_bfloat16> wpk;
+    pack_b_operand_f16e5(w_host, K, N, N, 0, &wpk);
+    DevBuf w;
+    CF_TRY(w.ensure(wpk.size() * 2));
+    CF_CUDA(cudaMemcpyAsync(w.ptr, wpk.data(), wpk.size() * 2, cudaMemcpyHostToDevice, stream));
+    const size_t smem = (size_t)128 * K * 4 + (size_t)N * K * 4 + 64;
+    CF_CUDA(cudaFuncSetAttribute(tc_selftest_f16e5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_selftest_f16e5_kernel<<<1, 128, smem, stream>>>(a_dev, w.as<uint8_t>(), K, N, mode, out_dev);
+    CF_LAUNCHED();
+    CF_CUDA(cudaStreamSynchronize(stream));
+    w.release();
     return CF_OK;
 }
 

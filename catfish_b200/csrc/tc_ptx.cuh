@@ -11,6 +11,8 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace cf {
@@ -122,6 +124,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
            | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// kind::f16 with A = B = fp16; and kind::f8f6f4 with A = B = e5m2 (format code 1, like bf16 above).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_e5m2(int m, int n) { return make_idesc_bf16(m, n); }
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -166,6 +174,28 @@ __device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t elected
         "setp.ne.b32 q, %1, 0;\n\t"
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
         "r"(elected)
+        : "memory");
+}
+
+// kind::f8f6f4 (8-bit operands, K = 32 per instruction, byte-identical descriptors to a K = 16 bf16 MMA)
+__device__ __forceinline__ void umma_f8_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts_pred(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
         : "memory");
 }
 
@@ -243,6 +273,38 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---------------------------------------------------------------- fp16 + e5m2 corrections ("f16e5")
+// x = h + l with h = fp16(x) (11 significant bits) and l the exact remainder.  A product a*w is
+// evaluated as  a_h*w_h  (one fp16 MMA)  +  [a_l*S | a_h/S] . [w_h/S ; w_l*S]  (one e5m2 MMA over the
+// doubled K, at twice the 16-bit rate): the two correction terms are 2^-12 of the product, so the
+// 3 significant bits of e5m2 keep the total near 2^-15; S = 2^6 puts both a_l*S (~2^-12 |a| S) and
+// a_h/S into e5m2's normal range (>= 2^-14) for every |a| >= 2^-8 - smaller values only carry
+// absolute errors below 2^-19 |w|.  Two pass-equivalents instead of the three of bf16x3 (tools/precision_emulation.py:
+// max |dp| 5.6e-5 vs 2.1e-5).
+constexpr float kCorrScale = 64.f;
+// Two values -> fp16x2 word (element 0 in the low half), e5m2x2 of the scaled remainders and
+// e5m2x2 of the down-scaled fp16 parts (element 0 in the low byte).
+__device__ __forceinline__ void split_f16e5x2(float x0, float x1, uint32_t& main, uint32_t& lo, uint32_t& hi) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    main = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    const float l0 = fmaf(hf.x, -kCorrScale, x0 * kCorrScale), l1 = fmaf(hf.y, -kCorrScale, x1 * kCorrScale);
+    lo = __nv_cvt_float2_to_fp8x2(make_float2(l0, l1), __NV_SATFINITE, __NV_E5M2);
+    const __half2 hs = __hmul2(h, __floats2half2_rn(1.f / kCorrScale, 1.f / kCorrScale));
+    hi = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);
+}
+// 16 values (one K = 16 chunk of an operand row): 8 fp16x2 words + 16 remainder bytes + 16 fp16-part bytes
+__device__ __forceinline__ void split_f16e5_chunk(const float* v, uint32_t* main, uint32_t* lo4, uint32_t* hi4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t la, ha, lb, hb;
+        split_f16e5x2(v[4 * j], v[4 * j + 1], main[2 * j], la, ha);
+        split_f16e5x2(v[4 * j + 2], v[4 * j + 3], main[2 * j + 1], lb, hb);
+        lo4[j] = la | (lb << 16);
+        hi4[j] = ha | (hb << 16);
+    }
 }
 
 // ---------------------------------------------------------------- activations (MUFU)

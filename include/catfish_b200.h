@@ -261,6 +261,16 @@ int cf_vote_events(int32_t device, const double* scores_dev, int64_t n_scores, c
 int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int32_t k, const float* wx_host,
                       const float* bias_host, float* out_dev, void* stream);
 
+/*
+ * cf_selftest_f16e5 - unit self-test of the fp16 + e5m2-correction MMA pair (no reference counterpart):
+ * out[w][n] = sum_k a[w][k] * w[k][n] for one tile of 128 rows, A split on the device into an fp16
+ * operand and an e5m2 operand of scaled remainders, placed in shared memory (mode 0) or tensor memory
+ * (mode 1); B packed on the host.  a_dev float32 [128][k], w_host [k][n], out_dev float32 [128][n];
+ * k in {16, 32, 48, 64}, n a multiple of 16 up to 128.  Synchronises.
+ */
+int cf_selftest_f16e5(int32_t device, const float* a_dev, int32_t k, int32_t n, const float* w_host, int32_t mode,
+                      float* out_dev, void* stream);
+
 /* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t cf_launch_count(void);
 

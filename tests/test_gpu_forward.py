@@ -129,8 +129,8 @@ def test_engine_cross_check_large():
 
 
 @pytest.mark.parametrize("env", [{"CF_TC_FUSED": "1"}, {"CF_TC_UNFUSED": "1"}, {"CF_TC_CONV": "1"}, {"CF_TC_CONV": "2"},
-                                 {"CF_TC_CONV": "3"}],
-                         ids=["one-tile-fused", "unfused-pair", "three-round-conv", "one-round-conv", "two-chain-conv-smem"])
+                                 {"CF_TC_CONV": "3"}, {"CF_TC_FMT": "0"}],
+                         ids=["one-tile-fused", "unfused-pair", "three-round-conv", "one-round-conv", "two-chain-conv-smem", "bf16x3-operands"])
 def test_tcgen05_kernel_variants(env, monkeypatch):
     """The alternative kernels of the tcgen05 engine (GRU: one tile per CTA; projection + recurrence
     as two kernels.  Conv stack: three rounds per position; one round; two chains with operands in
