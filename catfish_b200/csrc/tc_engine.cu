@@ -98,12 +98,15 @@ struct TcLayer {
     float* bx = nullptr;              // [384]
     __nv_bfloat16* wh = nullptr;      // [dir]{Wg hi, Wg lo [8][128][8]; Wc hi, Wc lo [8][64][8]}
     uint8_t* wfused = nullptr;        // [dir]{Wgx, Wcx, Wgh, Wch} as in GruFusedCfg (in = 32 or 128), exponent domain
+    uint8_t* wfused_bf = nullptr;     // bf16x3 twin when wfused is f16e5
     float* bz = nullptr;              // [384] biases in the exponent domain
 };
 
 struct TcEngine {
     SimtEngine* simt = nullptr;       // fp32 conv stack for shapes TK2 is not specialised for
     uint8_t* conv_params = nullptr;   // TK2 parameter block (see ConvParams), nullptr = use simt
+    uint8_t* conv_params_bf = nullptr;  // the same in bf16x3 when conv_params is f16e5 (out-of-range fallback)
+    int* fmt_flag = nullptr;          // device flag: 1 = this call's input is outside the fp16 format's safe range
     int conv_nres = 0;
     std::vector<TcLayer> layers;
     float* head_w = nullptr;          // [128]
@@ -158,9 +161,14 @@ TcEngine* tc_create(const HostModel& hm) {
                              e->conv_variant == 4 && e->fused_variant == 2 && e->use_fused;
         const char* env = getenv("CF_TC_FMT");
         e->fmt = covered && !(env && env[0] == '0') ? kFmtF16E5 : kFmtBf16x3;
+        if (e->fmt == kFmtF16E5) {
+            if (cudaMalloc(&e->fmt_flag, sizeof(int)) != cudaSuccess) e->fmt = kFmtBf16x3;
+            else e->owned.push_back(e->fmt_flag);
+        }
     }
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
-        // TK2 parameter block: fp32 vectors, then split-bf16 B operands (see ConvParams)
+        // TK2 parameter block: fp32 vectors, then the B operands in the given format (see ConvParams)
+        auto build_conv_block = [&](int fmt) {
         std::vector<uint8_t> blk(ConvParams::kBytes, 0);
         float* fp = reinterpret_cast<float*>(blk.data());
         auto put = [&](int slot, const std::vector<float>& v) { memcpy(fp + 32 * slot, v.data(), 32 * sizeof(float)); };
@@ -197,7 +205,7 @@ TcEngine* tc_create(const HostModel& hm) {
                 }
         };
         auto put_w = [&](int off, const float* w, int n, int ldw, int col0, int dst_col0, int n_total) {
-            if (e->fmt == kFmtF16E5) put_w_e5(off, w, n, ldw, col0, dst_col0, n_total);
+            if (fmt == kFmtF16E5) put_w_e5(off, w, n, ldw, col0, dst_col0, n_total);
             else put_w_bf(off, w, n, ldw, col0, dst_col0, n_total);
         };
         for (int tap = 0; tap < 3; ++tap) put_w(ConvParams::kW2 + tap * 4096, hm.convs[2].w.data() + tap * 32 * 32, 32, 32, 0, 0, 32);
@@ -209,7 +217,10 @@ TcEngine* tc_create(const HostModel& hm) {
             for (int tap = 0; tap < 3; ++tap) put_w(ConvParams::kW6 + tap * 4096, hm.convs[6].w.data() + tap * 32 * 32, 32, 32, 0, 0, 32);
             put_w(ConvParams::kW7, hm.convs[7].w.data(), 32, 32, 0, 0, 32);
         }
-        e->conv_params = tc_upload(e, blk);
+        return blk;
+        };
+        e->conv_params = tc_upload(e, build_conv_block(e->fmt));
+        if (e->fmt == kFmtF16E5) e->conv_params_bf = tc_upload(e, build_conv_block(kFmtBf16x3));
         e->conv_nres = hm.n_res();
     }
     for (int l = 0; l < hm.n_rnn(); ++l) {
@@ -242,17 +253,21 @@ TcEngine* tc_create(const HostModel& hm) {
         }
         L.wh = tc_upload(e, wh);
         if (L.in == kC || L.in == 2 * kH) {
-            std::vector<__nv_bfloat16> wf;
-            for (int d = 0; d < 2; ++d) {
-                const GruDir& g = hm.gru[2 * l + d];
-                // exponent domain: gates scaled by -log2(e), candidate by 2 log2(e) (see sigmoid4_z / tanh4_z)
-                // x rows of gates/kernel and candidate/kernel side by side: one N = 192 operand
-                auto pack = e->fmt == kFmtF16E5 ? pack_b_operand_f16e5 : pack_b_operand;
-                pack(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
-                pack(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale, 1 << 30, 1.f);
-                pack(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale, 1 << 30, 1.f);
-            }
-            L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, wf));
+            auto build_fused = [&](int fmt) {
+                std::vector<__nv_bfloat16> wf;
+                for (int d = 0; d < 2; ++d) {
+                    const GruDir& g = hm.gru[2 * l + d];
+                    // exponent domain: gates scaled by -log2(e), candidate by 2 log2(e) (see sigmoid4_z / tanh4_z)
+                    // x rows of gates/kernel and candidate/kernel side by side: one N = 192 operand
+                    auto pack = fmt == kFmtF16E5 ? pack_b_operand_f16e5 : pack_b_operand;
+                    pack(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
+                    pack(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale, 1 << 30, 1.f);
+                    pack(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale, 1 << 30, 1.f);
+                }
+                return wf;
+            };
+            L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, build_fused(e->fmt)));
+            if (e->fmt == kFmtF16E5) L.wfused_bf = reinterpret_cast<uint8_t*>(tc_upload(e, build_fused(kFmtBf16x3)));
             std::vector<float> bz(2 * kNX);
             for (int d = 0; d < 2; ++d)
                 for (int j = 0; j < kNX; ++j)
@@ -1089,7 +1104,10 @@ template <int FMT>
 __global__ void __launch_bounds__(576, 1)
 tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
                 const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
-                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out,
+                const int* __restrict__ fmt_flag) {
+    // two launches per pass when the engine runs f16e5: this one only if its format is the call's format
+    if (fmt_flag && ((*fmt_flag != 0) != (FMT == kFmtBf16x3))) return;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* prm = smem;
     uint8_t* o2 = smem + ConvParams::kBytes;
@@ -2025,7 +2043,8 @@ __global__ void __launch_bounds__(608, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
                      const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth,
-                     long long* __restrict__ trace) {
+                     long long* __restrict__ trace, const int* __restrict__ fmt_flag) {
+    if (fmt_flag && ((*fmt_flag != 0) != (FMT == kFmtBf16x3))) return;
     using Cfg = GruF2Cfg<KX>;
     // debug timeline (CF_TC_TRACE): block 0 records (tag, SM clock) pairs for steps 36..39 of each role
     int tr_n = 0;
@@ -2432,6 +2451,30 @@ __global__ void tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const f
     probs[src[g] + t] = p;
 }
 
+// ====================================================================== input range check (f16e5)
+// One thread per window: does any normalised sample of this call leave the range in which the fp16
+// operand format is safe (kF16SafeInput)?  Real signals stay within a few tens of MADs; a call that
+// does not (or that carries NaN / inf windows) is run by the bf16x3 twins of the kernels instead.
+__global__ void tc_range_flag_kernel(const int16_t* __restrict__ raw, const double* __restrict__ stats,
+                                     const float* __restrict__ xwin, const int64_t* __restrict__ src,
+                                     const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
+                                     int64_t n_windows, float limit, int* __restrict__ flag) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (g < n_windows) {
+        const int nv = valid[g];
+        const int64_t s0 = src[g];
+        if (nv > 0 && raw) {
+            const int r = read[g];
+            const double shift = stats[2 * r], lim = (double)limit * stats[2 * r + 1];
+            for (int t = 0; t < nv; ++t) bad |= !(fabs((double)raw[s0 + t] - shift) <= lim);
+        } else if (nv > 0) {
+            for (int t = 0; t < nv; ++t) bad |= !(fabsf(xwin[s0 + t]) <= limit);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 // ====================================================================== forward
 int simt_conv_stack(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats, const float* xwin,
                     WindowTable tab, int64_t tile0, int64_t tiles, int64_t chunk_tiles, const float** feat,
@@ -2485,6 +2528,14 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
     float* head_part = reinterpret_cast<float*>(p);
 
     const int n_layers = (int)e->layers.size();
+    if (e->fmt == kFmtF16E5) {
+        ProfScope ps(prof, KC_K1_TABLE, stream);
+        CF_CUDA(cudaMemsetAsync(e->fmt_flag, 0, sizeof(int), stream));
+        const int64_t n_windows = n_tiles * kTileWindows;
+        tc_range_flag_kernel<<<(unsigned)ceil_div(n_windows, (int64_t)256), 256, 0, stream>>>(
+            raw, raw ? stats : nullptr, xwin, tab.src, tab.valid, tab.read, n_windows, kF16SafeInput, e->fmt_flag);
+        CF_LAUNCHED();
+    }
     for (int64_t tile0 = 0; tile0 < n_tiles; tile0 += kTcChunkTiles) {
         const int64_t tiles = std::min<int64_t>(kTcChunkTiles, n_tiles - tile0);
         const int64_t blocks = tiles * kWindow;
@@ -2495,12 +2546,16 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             ProfScope ps(prof, KC_K2_CONV, stream);
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
             if (e->conv_variant == 4 && e->conv_nres == 2) {
-                if (e->fmt == kFmtF16E5)
+                if (e->fmt == kFmtF16E5) {
                     tc_conv4_kernel<1><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0);
-                else
+                                                                         tab.read, tile0, (int)tiles, a0, e->fmt_flag);
+                    CF_LAUNCHED();
+                    tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params_bf, raw, stats, xwin, tab.src, tab.valid,
+                                                                         tab.read, tile0, (int)tiles, a0, e->fmt_flag);
+                } else {
                     tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0);
+                                                                         tab.read, tile0, (int)tiles, a0, nullptr);
+                }
             } else if (e->conv_variant >= 3 && e->conv_nres == 2) {
                 tc_conv3_kernel<<<grid, 576, kConv3Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                   tab.read, tile0, (int)tiles, a0);
@@ -2546,18 +2601,26 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
                     const float* hw_l = last ? e->head_w : nullptr;
                     float* hp_l = last ? head_part : nullptr;
-                    if (L.in == kC && e->fmt == kFmtF16E5)
-                        tc_gru_fused2_kernel<32, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
-                    else if (L.in == kC)
+                    const bool e5 = e->fmt == kFmtF16E5;
+                    const int* flag = e5 ? e->fmt_flag : nullptr;
+                    const uint8_t* w_bf = e5 ? L.wfused_bf : L.wfused;
+                    if (L.in == kC) {
+                        if (e5) {
+                            tc_gru_fused2_kernel<32, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr, flag);
+                            CF_LAUNCHED();
+                        }
                         tc_gru_fused2_kernel<32, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
-                    else if (e->fmt == kFmtF16E5)
-                        tc_gru_fused2_kernel<128, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
-                    else
+                            w_bf, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr, flag);
+                    } else {
+                        if (e5) {
+                            tc_gru_fused2_kernel<128, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev, flag);
+                            CF_LAUNCHED();
+                        }
                         tc_gru_fused2_kernel<128, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
+                            w_bf, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, e5 ? nullptr : trace_dev, flag);
+                    }
                     CF_LAUNCHED();
                     if (trace_dev) {
                         // debug: dump the timeline of block 0 and stop tracing

@@ -226,3 +226,26 @@ def test_rnn_stress_variant_h256_five_layers_simt():
     got = m.infer(x)
     want = tf_graph.forward_np(w, x, np.float64)
     assert np.abs(got - want).max() < PROB_TOL
+
+
+def test_outlier_samples_stay_finite_and_in_contract():
+    """Raw spikes thousands of MADs away from the median (the fp16 operand format must not overflow):
+    the tcgen05 engine still agrees with the fp32 engine and the CPU oracle."""
+    rng = np.random.default_rng(9)
+    reads = []
+    for k, mad in enumerate((1, 3, 20)):
+        raw = (500 + np.rint(rng.normal(0, mad * 1.4826, 6000))).astype(np.int16)
+        idx = rng.choice(raw.size, 12, replace=False)
+        raw[idx[:6]] = 32767
+        raw[idx[6:]] = -32768
+        reads.append(raw)
+    m = _model("ResNetRNN", "auto")
+    ref = _model("ResNetRNN", "simt")
+    _, _, s1 = infer.infer_reads(reads, m, return_scores=True)
+    _, _, s2 = infer.infer_reads(reads, ref, return_scores=True)
+    graph = tf_graph.TorchGraph(weights.load_shipped())
+    for raw, a, b in zip(reads, s1, s2):
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() < PROB_TOL
+        _, _, want = postprocess.infer_read(raw, graph.infer)
+        assert np.abs(a - want).max() < PROB_TOL
