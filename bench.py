@@ -346,7 +346,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (split bf16 operands, fp32 accumulate)" if engine == "tcgen05" else "f32",
+            "dtype": {"f16e5": "f16+e5m2 (fp16 product + e5m2 correction product, fp32 accumulate)",
+                      "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)"}.get(model.operand_format, "f32"),
             "data": "synthetic", "config": workload_config(n_reads, engine),
             "reads_per_sec": world * n_reads * args.steps / (ms_dev * 1e-3),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

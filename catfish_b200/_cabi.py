@@ -44,6 +44,7 @@ SIGNATURES = {
     "cf_model_destroy": (None, [c_void]),
     "cf_model_num_tensors": (ctypes.c_int, [ctypes.POINTER(ModelDesc)]),
     "cf_model_engine": (ctypes.c_int, [c_void]),
+    "cf_model_operand_format": (ctypes.c_int, [c_void]),
     "cf_model_reserve": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int32]),
     "cf_infer_windows": (ctypes.c_int, [c_void, c_void, ctypes.c_int64, c_void, c_void]),
     "cf_infer_reads": (ctypes.c_int, [c_void, c_void, c_i64_p, ctypes.c_int32, c_void, c_void, c_void,

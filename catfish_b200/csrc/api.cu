@@ -626,6 +626,10 @@ void cf_model_destroy(cf_model* m) {
 }
 
 int cf_model_engine(const cf_model* m) { return m ? m->engine : CF_ERR_BAD_ARG; }
+int cf_model_operand_format(const cf_model* m) {
+    if (!m) return CF_ERR_BAD_ARG;
+    return m->engine == CF_ENGINE_TCGEN05 ? cf::tc_operand_format(m->tc) : -1;
+}
 
 int cf_profile_enable(cf_model* m, int32_t on) {
     if (!m) { cf::set_error("cf_profile_enable: NULL model"); return CF_ERR_BAD_ARG; }

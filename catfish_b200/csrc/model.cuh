@@ -62,6 +62,7 @@ struct TcEngine;
 bool tc_supported(const HostModel& hm);
 TcEngine* tc_create(const HostModel& hm);
 void tc_destroy(TcEngine* e);
+int tc_operand_format(const TcEngine* e);    // 0 = split bf16 (3 MMA passes), 1 = fp16 + e5m2 corrections (2 pass-equivalents)
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
                cudaStream_t stream, Profiler* prof, bool want_logits = false);

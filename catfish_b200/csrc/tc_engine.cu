@@ -219,8 +219,8 @@ TcEngine* tc_create(const HostModel& hm) {
         }
         return blk;
         };
-        e->conv_params = tc_upload(e, build_conv_block(e->fmt));
-        if (e->fmt == kFmtF16E5) e->conv_params_bf = tc_upload(e, build_conv_block(kFmtBf16x3));
+        e->conv_params = tc_upload(e, build_conv_block(kFmtBf16x3));    // the conv stack is bf16x3 inside for both formats
+        e->conv_params_bf = e->conv_params;
         e->conv_nres = hm.n_res();
     }
     for (int l = 0; l < hm.n_rnn(); ++l) {
@@ -280,6 +280,8 @@ TcEngine* tc_create(const HostModel& hm) {
     e->head_b = hm.head_b;
     return e;
 }
+
+int tc_operand_format(const TcEngine* e) { return e ? e->fmt : 0; }
 
 void tc_destroy(TcEngine* e) {
     if (!e) return;
@@ -1106,7 +1108,10 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
                 const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out,
                 const int* __restrict__ fmt_flag) {
-    // two launches per pass when the engine runs f16e5: this one only if its format is the call's format
+    // FMT is the format of the OUTPUT (the first GRU layer's x operand); inside the stack every operand is
+    // split bf16 - the epilogue, not the tensor pipe, bounds this kernel and the bf16 split is the cheaper one.
+    // Two launches per pass when the engine runs f16e5: this one only if its format is the call's format.
+    constexpr int kInt = kFmtBf16x3;
     if (fmt_flag && ((*fmt_flag != 0) != (FMT == kFmtBf16x3))) return;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* prm = smem;
@@ -1163,11 +1168,11 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     for (int tap = 0; tap < 3; ++tap) {
                         const int tt = t1 + tap - 1;
                         if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_ts_pred<32, FMT>(tmem + 0, tmem + kTmO1 + (tt & 3) * 32, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
+                        conv_mma_ts_pred<32, kInt>(tmem + 0, tmem + kTmO1 + (tt & 3) * 32, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
                         first = false;
                     }
                 }
-                if (t2 >= 0 && t2 < kWindow) conv_mma_f<32, FMT>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
+                if (t2 >= 0 && t2 < kWindow) conv_mma_f<32, kInt>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
                 umma_commit_pred(bar_mma_x, elected);
             }
         }
@@ -1184,7 +1189,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 if (t3 < kWindow) {
                     mbar_wait(&bar_y0_full[ny_slot], ny_par);
                     tc_fence_after_sync();
-                    conv_mma_ts_pred<64, FMT>(tmem + kTmScp1, tmem + kTmY0 + ny_slot * 32, prm_u + ConvParams::kW45, true, elected);
+                    conv_mma_ts_pred<64, kInt>(tmem + kTmScp1, tmem + kTmY0 + ny_slot * 32, prm_u + ConvParams::kW45, true, elected);
                     umma_commit_pred(&bar_y0_empty[ny_slot], elected);
                     ++ny;
                     if (++ny_slot == 3) { ny_slot = 0; ny_par ^= 1; }
@@ -1195,11 +1200,11 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     for (int tap = 0; tap < 3; ++tap) {
                         const int tt = t4 + tap - 1;
                         if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_ts_pred<32, FMT>(tmem + 64, tmem + kTmP1 + (tt % 3) * 32, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
+                        conv_mma_ts_pred<32, kInt>(tmem + 64, tmem + kTmP1 + (tt % 3) * 32, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
                         first = false;
                     }
                 }
-                if (t5 >= 0 && t5 < kWindow) conv_mma_f<32, FMT>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
+                if (t5 >= 0 && t5 < kWindow) conv_mma_f<32, kInt>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
                 umma_commit_pred(bar_mma_y, elected);
             }
         }
@@ -1228,7 +1233,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
-                store_a_tmem16_f<FMT>(t_opnd + kTmO1 + (t & 3) * 32, v);
+                store_a_tmem16_f<kInt>(t_opnd + kTmO1 + (t & 3) * 32, v);
             };
             uint32_t it = 0, ny = 0, ny_slot = 0, ny_par = 1;      // empty-barrier parity of the previous use
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1265,7 +1270,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     if (h2) tmem_ld16_nowait(t_lane + 32, r2);
                     tmem_ld_wait();
                     float v[16];
-                    if (h1) { relu_bias(r1, 4, v); store_a_row16_f<FMT>(o2, row, c0, v); }              // b2
+                    if (h1) { relu_bias(r1, 4, v); store_a_row16_f<kInt>(o2, row, c0, v); }              // b2
                     // o2 and o1[u+1] (made one iteration ago, in TMEM) are all the next X batch reads
                     if (u < kLastX) {
                         fence_proxy_async_smem();
@@ -1281,7 +1286,7 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
                         if (ny >= 3) mbar_wait(&bar_y0_empty[ny_slot], ny_par);
                         tc_fence_after_sync();
-                        store_a_tmem16_f<FMT>(t_opnd + kTmY0 + ny_slot * 32, v);
+                        store_a_tmem16_f<kInt>(t_opnd + kTmY0 + ny_slot * 32, v);
                         tmem_st_wait();
                         tc_fence_before_sync();
                         __syncwarp();
@@ -1312,8 +1317,8 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     if (h5) tmem_ld16_nowait(t_lane + 96, r5);
                     tmem_ld_wait();
                     float v[16];
-                    if (h3) { relu_bias(r3, 7, v); store_a_tmem16_f<FMT>(t_opnd + kTmP1 + (t3 % 3) * 32, v); }   // b5
-                    if (h4) { relu_bias(r4, 8, v); store_a_row16_f<FMT>(p2, row, c0, v); }              // b6
+                    if (h3) { relu_bias(r3, 7, v); store_a_tmem16_f<kInt>(t_opnd + kTmP1 + (t3 % 3) * 32, v); }   // b5
+                    if (h4) { relu_bias(r4, 8, v); store_a_row16_f<kInt>(p2, row, c0, v); }              // b6
                     fence_proxy_async_smem();
                     tmem_st_wait();
                     tc_fence_before_sync();

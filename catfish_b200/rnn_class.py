@@ -115,6 +115,11 @@ class RNN(object):
     def resolved_engine(self):
         return _cabi.ENGINE_NAMES[_cabi.load_library().cf_model_engine(self.handle)]
 
+    @property
+    def operand_format(self):
+        """"f16e5" (fp16 + e5m2 correction MMAs), "bf16x3" (split bf16) or "f32" (CUDA-core engine)."""
+        return {1: "f16e5", 0: "bf16x3"}.get(_cabi.load_library().cf_model_operand_format(self.handle), "f32")
+
     def infer(self, input_x):
         """rnn_class.py:213-219: ``input_x`` [n_windows, 35, 1] -> float64 [n_windows * 35]."""
         import torch

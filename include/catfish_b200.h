@@ -88,6 +88,10 @@ int cf_model_num_tensors(const cf_model_desc* desc);
 
 /* Which engine the handle resolved to (cf_engine value). */
 int cf_model_engine(const cf_model* model);
+/* Tensor-core operand format of the handle: 0 = split bf16, three MMA passes ("bf16x3"); 1 = fp16 main
+ * product + e5m2 correction product, two pass-equivalents ("f16e5", the default where every kernel of
+ * the pass supports it; CF_TC_FMT=0 in the environment forces 0); -1 = fp32 CUDA-core engine. */
+int cf_model_operand_format(const cf_model* model);
 
 /* Pre-size the handle's workspace so later calls do not allocate
  * (max total samples / reads per call).  Optional. */

@@ -23,11 +23,15 @@ if __name__ == "__main__":
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    it = hdr.index("gpu__time_duration.sum")
+    TU = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
     acc = {}
     for r in rows[2:]:
         name = r[ik]
         cls = next((v for k, v in CLASSES.items() if k in name), None)
         if cls is None:
+            continue
+        if float(r[it]) * TU.get(units[it], 1.0) < 20.0:      # early-exit twin of the other operand format
             continue
         b = float(r[ir]) * UNITS[units[ir]] + float(r[iw]) * UNITS[units[iw]]
         acc.setdefault(cls, []).append(b)

@@ -22,7 +22,12 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
+    it = hdr.index("gpu__time_duration.sum")
+    tu = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
     for r in rows[2:]:
+        if float(r[it]) * tu.get(units[it], 1.0) < 20.0:
+            print("== kernel (early exit, %s %s):" % (r[it], units[it]), r[hdr.index("Kernel Name")][:70])
+            continue
         print("== kernel:", r[hdr.index("Kernel Name")][:90])
         for h, u, v in zip(hdr, units, r):
             if any(k.strip() in h for k in KEYS if not k.endswith(" ")) or any(h == k.strip() for k in KEYS if k.endswith(" ")):
