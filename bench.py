@@ -272,7 +272,12 @@ def run_b200(args):
     # ---- timed region 1: device-resident inputs, per-kernel-class events on
     _cabi.profile_enable(handle, True)
     launches0 = _cabi.launch_count()
-    sampler = ClockSampler(local_rank)
+    # address the GPU by UUID: nvidia-smi's index order need not be CUDA's (visible-device remapping)
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_id = local_rank
+    sampler = ClockSampler(gpu_id)
     t0 = time.time()
     ms_dev = timed(step_device, args.steps)
     t1 = time.time()

@@ -249,3 +249,19 @@ def test_outlier_samples_stay_finite_and_in_contract():
         assert np.abs(a - b).max() < PROB_TOL
         _, _, want = postprocess.infer_read(raw, graph.infer)
         assert np.abs(a - want).max() < PROB_TOL
+
+
+def test_outlier_windows_stay_in_contract():
+    """Same through the window-level entry point (cf_infer_windows), including a non-finite window."""
+    rng = np.random.default_rng(10)
+    x = rng.normal(0, 1.5, size=(200, 35, 1)).astype(np.float32)
+    x[17, 5, 0] = 4.0e4
+    x[90, 30, 0] = -2.5e4
+    m, ref = _model("ResNetRNN", "auto"), _model("ResNetRNN", "simt")
+    a, b = m.infer(x), ref.infer(x)
+    assert np.isfinite(a).all() and np.abs(a - b).max() < PROB_TOL
+    assert m.operand_format in ("f16e5", "bf16x3") and ref.operand_format == "f32"
+    x[3, 0, 0] = np.inf
+    a, b = m.infer(x).reshape(200, 35), ref.infer(x).reshape(200, 35)
+    keep = np.arange(200) != 3                       # windows are independent: only window 3 may be non-finite
+    assert np.isfinite(a[keep]).all() and np.abs(a[keep] - b[keep]).max() < PROB_TOL
