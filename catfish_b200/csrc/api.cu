@@ -815,11 +815,17 @@ int cf_infer_reads_host(cf_model* m, const int16_t* raw_host, const int64_t* off
         CF_TRY(m->h_probs.ensure(sizeof(float) * (size_t)(total > 0 ? total : 1)));
         probs_dev = m->h_probs.as<float>();
     }
-    if (total > 0)
-        CF_CUDA(cudaMemcpyAsync(m->h_raw.ptr, raw_host + base, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, st));
     // offsets rebased so that raw_dev + offsets[0] is the staged copy
     std::vector<int64_t> off((size_t)n_reads + 1);
     for (int32_t i = 0; i <= n_reads; ++i) off[i] = offsets_host[i] - base;
+    {
+        cf::BatchPlan whole;                       // reject bad / empty reads before any asynchronous copy reads the caller's buffer
+        CF_TRY(cf::make_plan(off.data(), n_reads, &whole));
+    }
+    // (Cutting the batch into groups of whole passes whose copies overlap the previous group's kernels was
+    // measured: no gain - the copy is 1.2-1.5 ms of a 75 ms step and the extra K1 / K6 sequences cost as much.)
+    if (total > 0)
+        CF_CUDA(cudaMemcpyAsync(m->h_raw.ptr, raw_host + base, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, st));
     CF_TRY(cf::infer_reads_device(m, m->h_raw.as<int16_t>(), off.data(), n_reads, probs_dev,
                                   m->h_intervals.as<int64_t>(), m->h_ioff.as<int64_t>(), capacity, threshold,
                                   min_run, ext_left, ext_right, st));

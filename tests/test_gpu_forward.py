@@ -265,3 +265,21 @@ def test_outlier_windows_stay_in_contract():
     a, b = m.infer(x).reshape(200, 35), ref.infer(x).reshape(200, 35)
     keep = np.arange(200) != 3                       # windows are independent: only window 3 may be non-finite
     assert np.isfinite(a[keep]).all() and np.abs(a[keep] - b[keep]).max() < PROB_TOL
+
+
+def test_large_host_call_equals_smaller_calls():
+    """A batch of several engine passes through cf_infer_reads_host: CSR offsets, intervals and probabilities
+    equal those of smaller calls over sub-ranges of the same reads (batch invariance at the host boundary)."""
+    m = _model("ResNetRNN", "auto")
+    lengths = synth.ragged_lengths(300, 60_000, 120_000, seed=3)           # ~27M samples = 5 passes
+    reads = synth.synth_reads(lengths, base_seed=9000)
+    raw, off = synth.concat_reads(reads)
+    iv, ioff, scores = infer.infer_concatenated(raw, off, m, return_scores=True)
+    assert ioff[0] == 0 and ioff[-1] == len(iv) and np.all(np.diff(ioff) >= 0)
+    for lo, hi in ((0, 40), (130, 170), (260, 300)):
+        sub_raw = raw[off[lo]:off[hi]]
+        sub_off = off[lo:hi + 1] - off[lo]
+        iv2, ioff2, scores2 = infer.infer_concatenated(sub_raw, sub_off, m, return_scores=True)
+        assert np.array_equal(ioff2, ioff[lo:hi + 1] - ioff[lo])
+        assert np.array_equal(iv2, iv[ioff[lo]:ioff[hi]])
+        assert np.array_equal(scores2, scores[off[lo]:off[hi]])
