@@ -1,21 +1,29 @@
 // tcgen05 engine: the GEMM-shaped part of the forward graph on 5th-gen tensor cores.
 //
 // Specialised for the shipped hyper-parameters (conv channels C = 32, GRU units H = 64; any
-// number of layers; network types ResNetRNN and RNN).  Every product is evaluated in split
-// bf16 ("bf16x3": a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32 accumulate in TMEM) because single
-// bf16/fp16 operands do not meet the 1e-3 probability contract (precision table).
+// number of layers; network types ResNetRNN, RNN and ResNet).  Single bf16/fp16 operands do not
+// meet the 1e-3 probability contract (precision table), so every product is evaluated
+// with split operands and fp32 accumulation in TMEM, in one of two formats:
+//   bf16x3  a_hi w_hi + a_lo w_hi + a_hi w_lo, three kind::f16 MMAs per K = 16 chunk
+//   f16e5   fp16 product + one e5m2 MMA over [a_l S | a_h / S] [w_h / S ; w_l S]: two
+//           pass-equivalents (default for the fused GRU layers of ResNetRNN; tc_ptx.cuh)
 //
-//   TK3  tc_xproj_kernel  GRU input projection  xp = y W_x + b   (rnn_class.py:146,170: the
-//        x rows of gates/kernel and candidate/kernel, hoisted out of the time loop)
-//   TK4  tc_gru_kernel    GRU recurrence over the 35 steps of a window tile, both directions
-//        as two independent chains per CTA, recurrent weights resident in shared memory,
-//        gates/activations fused in the TMEM epilogue (rnn_class.py:142-175)
-//   TK5  tc_head_kernel   dense 128 -> 1 + sigmoid from the per-direction partial dots that
-//        the last layer's TK4 epilogue produces (rnn_class.py:178-183, 84)
+// Default path of a pass (at most kTcChunkTiles tiles):
+//   TK2   tc_conv4_kernel        residual conv stack, two chains, operands in tensor memory
+//   TK4G  tc_gru_fused2_kernel   one GRU layer (input projection + recurrence), two tiles per CTA
+//   TK5   tc_head_kernel         dense 128 -> 1 + sigmoid from the partial dots of the last layer
+// preceded once per call by tc_range_flag_kernel (f16e5 only: fall back to the bf16x3 twins when the
+// input leaves fp16's safe range).  Cross-checks / other shapes: tc_conv_kernel, tc_conv2_kernel,
+// tc_conv3_kernel (CF_TC_CONV=1..3), tc_gru_fused_kernel (CF_TC_FUSED=1), and the unfused pair
+//   TK3   tc_xproj_kernel  GRU input projection  xp = y W_x + b   (rnn_class.py:146,170: the
+//         x rows of gates/kernel and candidate/kernel, hoisted out of the time loop)
+//   TK4   tc_gru_kernel    GRU recurrence over the 35 steps of a window tile, both directions
+//         as two independent chains per CTA (rnn_class.py:142-175)
+// (CF_TC_UNFUSED=1, and layer 0 of RNN-only networks whose input is 1 wide).
 //
 // Data layout: a tile is 128 windows (= 128 TMEM lanes = UMMA M); a block is (tile, t), one of
 // the 35 positions of those windows.  Activations that feed an MMA live in global memory as
-// ready-made UMMA operands: per block a hi plane then a lo plane, each [K/8][128][8] bf16, so a
+// ready-made UMMA operands: per block plane 0 then plane 1, each [K/8][128][16 bytes], so a
 // block is one contiguous cp.async.bulk (TMA) copy.  xp is stored per block as [384][128] fp32
 // (column-major), which makes both its producer (TMEM lane = window) and its consumer coalesced.
 #include <algorithm>
@@ -2021,10 +2029,10 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
 // Same mathematics as TK4F, restructured so that the tensor pipe never idles behind one chain's
 // serial MMA -> epilogue -> MMA dependency: a CTA runs TWO independent chains (two tiles of the
 // same direction, sharing the resident weights).  To make room for the second chain the state
-// operand h / r*h no longer lives in shared memory: the epilogue writes it (split bf16, packed)
-// into tensor memory with tcgen05.st and the state-part MMAs read A from TMEM (".ts" form).
-// TMEM per chain (256 columns): gates accumulator 0..127, candidate 128..191, A hi 192..223,
-// A lo 224..255.  Shared memory: weights (147 KB) + one 5-stage x ring per chain (80 KB).
+// operand h / r*h no longer lives in shared memory: the epilogue writes it (packed, in the operand
+// format FMT) into tensor memory with tcgen05.st and the state-part MMAs read A from TMEM (".ts" form).
+// TMEM per chain (256 columns): gates accumulator 0..127, candidate 128..191, A plane 0 192..223,
+// A plane 1 224..255.  Shared memory: weights (147 KB) + one 5-stage x ring per chain (80 KB).
 //   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
 //   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
 //   warp 18          : lanes 0 / 1 = producer of chain 0 / 1 (weights once, then the chain's x ring)
