@@ -2252,11 +2252,20 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         const uint32_t t_alo = t_ahi + 32;
         const float* hw = head_w ? head_w + dir * kH + j0 : nullptr;
         const int my_tiles = tiles_of(chain);
+#ifndef CF_PRECISE_ACT
+        float2 h2[16], u2[16];                 // state and update gate of this thread's 32 units, as packed pairs
+#else
         float h[32], u[32];
+#endif
         int gs = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
+#ifndef CF_PRECISE_ACT
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h2[j] = make_float2(0.f, 0.f);
+#else
 #pragma unroll
             for (int j = 0; j < 32; ++j) h[j] = 0.f;
+#endif
             {
                 const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 tmem_st8_u32(t_ahi, z);
@@ -2285,18 +2294,20 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
-                            float r[4];
                             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + c0 + i);
 #ifndef CF_PRECISE_ACT
-                            r[0] = sigmoid_zb(__uint_as_float(ar[c0 + i]), b4.x); r[1] = sigmoid_zb(__uint_as_float(ar[c0 + i + 1]), b4.y);
-                            r[2] = sigmoid_zb(__uint_as_float(ar[c0 + i + 2]), b4.z); r[3] = sigmoid_zb(__uint_as_float(ar[c0 + i + 3]), b4.w);
+                            const float2 r0 = sigmoid_zb2(make_float2(__uint_as_float(ar[c0 + i]), __uint_as_float(ar[c0 + i + 1])), make_float2(b4.x, b4.y));
+                            const float2 r1 = sigmoid_zb2(make_float2(__uint_as_float(ar[c0 + i + 2]), __uint_as_float(ar[c0 + i + 3])), make_float2(b4.z, b4.w));
+                            const float2 p0 = fmul2(r0, h2[(c0 + i) >> 1]), p1 = fmul2(r1, h2[((c0 + i) >> 1) + 1]);
+                            split4<FMT>(p0.x, p0.y, p1.x, p1.y, i, hi, lo);
 #else
+                            float r[4];
                             float z[4];
                             z[0] = __uint_as_float(ar[c0 + i]) + b4.x; z[1] = __uint_as_float(ar[c0 + i + 1]) + b4.y;
                             z[2] = __uint_as_float(ar[c0 + i + 2]) + b4.z; z[3] = __uint_as_float(ar[c0 + i + 3]) + b4.w;
                             sigmoid4_z(z, r);
-#endif
                             split4<FMT>(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], i, hi, lo);
+#endif
                         }
                         tmem_st8_u32(t_ahi + c0 / 2, hi);
                         tmem_st8_u32(t_alo + c0 / 2, lo);
@@ -2317,8 +2328,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     for (int i = 0; i < 32; i += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + kH + j0 + i);
 #ifndef CF_PRECISE_ACT
-                        u[i] = sigmoid_zb(__uint_as_float(au[i]), b4.x); u[i + 1] = sigmoid_zb(__uint_as_float(au[i + 1]), b4.y);
-                        u[i + 2] = sigmoid_zb(__uint_as_float(au[i + 2]), b4.z); u[i + 3] = sigmoid_zb(__uint_as_float(au[i + 3]), b4.w);
+                        u2[i >> 1] = sigmoid_zb2(make_float2(__uint_as_float(au[i]), __uint_as_float(au[i + 1])), make_float2(b4.x, b4.y));
+                        u2[(i >> 1) + 1] = sigmoid_zb2(make_float2(__uint_as_float(au[i + 2]), __uint_as_float(au[i + 3])), make_float2(b4.z, b4.w));
 #else
                         float z[4];
                         z[0] = __uint_as_float(au[i]) + b4.x; z[1] = __uint_as_float(au[i + 1]) + b4.y;
@@ -2343,20 +2354,28 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    float cv[4];
                     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * kH + j0 + i);
 #ifndef CF_PRECISE_ACT
-                    cv[0] = tanh_zb(__uint_as_float(ac[i]), b4.x); cv[1] = tanh_zb(__uint_as_float(ac[i + 1]), b4.y);
-                    cv[2] = tanh_zb(__uint_as_float(ac[i + 2]), b4.z); cv[3] = tanh_zb(__uint_as_float(ac[i + 3]), b4.w);
+                    {
+                        // h = c + u (h - c), two units per instruction
+                        const float2 c0v = tanh_zb2(make_float2(__uint_as_float(ac[i]), __uint_as_float(ac[i + 1])), make_float2(b4.x, b4.y));
+                        const float2 c1v = tanh_zb2(make_float2(__uint_as_float(ac[i + 2]), __uint_as_float(ac[i + 3])), make_float2(b4.z, b4.w));
+                        float2& ha = h2[i >> 1];
+                        float2& hb = h2[(i >> 1) + 1];
+                        ha = ffma2(u2[i >> 1], ffma2(c0v, splat2(-1.f), ha), c0v);
+                        hb = ffma2(u2[(i >> 1) + 1], ffma2(c1v, splat2(-1.f), hb), c1v);
+                        split4<FMT>(ha.x, ha.y, hb.x, hb.y, i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
+                    }
 #else
+                    float cv[4];
                     float z[4];
                     z[0] = __uint_as_float(ac[i]) + b4.x; z[1] = __uint_as_float(ac[i + 1]) + b4.y;
                     z[2] = __uint_as_float(ac[i + 2]) + b4.z; z[3] = __uint_as_float(ac[i + 3]) + b4.w;
                     tanh4_z(z, cv);
-#endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
                     split4<FMT>(h[i], h[i + 1], h[i + 2], h[i + 3], i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
+#endif
                 }
                 tmem_st8_u32(t_ahi, hi);
                 tmem_st8_u32(t_ahi + 8, hi + 8);
@@ -2379,9 +2398,16 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     }
                 }
                 if (head_part) {
+#ifndef CF_PRECISE_ACT
+                    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc2 = ffma2(h2[i], __ldg(reinterpret_cast<const float2*>(hw) + i), acc2);
+                    const float acc = acc2.x + acc2.y;
+#else
                     float acc = 0.f;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc = fmaf(h[i], __ldg(hw + i), acc);
+#endif
                     head_part[((blk * 2 + dir) * 2 + hf) * 128 + row] = acc;
                 }
             }

@@ -275,6 +275,36 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FADD2 / FMUL2)
+// sm_100 executes two fp32 operations per lane in one instruction: half the issue slots for the
+// epilogues' elementwise math (they are bound by instruction issue, not by the FMA pipe).
+__device__ __forceinline__ uint64_t pack2(float2 a) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t r) {
+    float2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)), "l"(pack2(c)));
+    return unpack2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(d);
+}
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+
 // ---------------------------------------------------------------- fp16 + e5m2 corrections ("f16e5")
 // x = h + l with h = fp16(x) (11 significant bits) and l the exact remainder.  A product a*w is
 // evaluated as  a_h*w_h  (one fp16 MMA)  +  [a_l*S | a_h/S] . [w_h/S ; w_l*S]  (one e5m2 MMA over the
@@ -294,9 +324,8 @@ constexpr float kF16SafeInput = 1000.f;
 __device__ __forceinline__ void split_f16e5x2(float x0, float x1, uint32_t& main, uint32_t& lo, uint32_t& hi) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(main) : "f"(x1), "f"(x0));   // saturating: no infinities
     const __half2 h = *reinterpret_cast<const __half2*>(&main);
-    const float2 hf = __half22float2(h);
-    const float l0 = fmaf(hf.x, -kCorrScale, x0 * kCorrScale), l1 = fmaf(hf.y, -kCorrScale, x1 * kCorrScale);
-    lo = __nv_cvt_float2_to_fp8x2(make_float2(l0, l1), __NV_SATFINITE, __NV_E5M2);
+    const float2 l = ffma2(__half22float2(h), splat2(-kCorrScale), fmul2(make_float2(x0, x1), splat2(kCorrScale)));
+    lo = __nv_cvt_float2_to_fp8x2(l, __NV_SATFINITE, __NV_E5M2);
     const __half2 hs = __hmul2(h, __floats2half2_rn(1.f / kCorrScale, 1.f / kCorrScale));
     hi = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);
 }
@@ -381,6 +410,15 @@ constexpr float kSigArgScale = -0.34657359027997264f;     // z * (-ln2 / 2): sig
 constexpr float kTanhArgScale = 0.34657359027997264f;      // z * ( ln2 / 2): tanh(x)
 __device__ __forceinline__ float sigmoid_zb(float acc, float bk) { return fmaf(tanh_approx(fmaf(acc, kSigArgScale, bk)), 0.5f, 0.5f); }
 __device__ __forceinline__ float tanh_zb(float acc, float bk) { return tanh_approx(fmaf(acc, kTanhArgScale, bk)); }
+// two values at a time: packed argument / result arithmetic around the two MUFU.TANH
+__device__ __forceinline__ float2 sigmoid_zb2(float2 acc, float2 bk) {
+    const float2 z = ffma2(acc, splat2(kSigArgScale), bk);
+    return ffma2(make_float2(tanh_approx(z.x), tanh_approx(z.y)), splat2(0.5f), splat2(0.5f));
+}
+__device__ __forceinline__ float2 tanh_zb2(float2 acc, float2 bk) {
+    const float2 z = ffma2(acc, splat2(kTanhArgScale), bk);
+    return make_float2(tanh_approx(z.x), tanh_approx(z.y));
+}
 #endif
 #ifndef CF_PRECISE_ACT
 // Default: MUFU.TANH based activations, one MUFU + one FMA-pipe instruction per gate value.
