@@ -1228,19 +1228,25 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(fp + 32 * slot + c0 + i);
-                v[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
-                v[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
-                v[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
-                v[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+                const float2 s0 = fadd2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(b4.x, b4.y));
+                const float2 s1 = fadd2(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), make_float2(b4.z, b4.w));
+                v[i] = fmaxf(s0.x, 0.f);
+                v[i + 1] = fmaxf(s0.y, 0.f);
+                v[i + 2] = fmaxf(s1.x, 0.f);
+                v[i + 3] = fmaxf(s1.y, 0.f);
             }
         };
         if (warp < 8) {
             // -------------------------------------------------------- epilogue of chain X
             auto make_o1 = [&](int t) {               // o1[t] = relu(x a1 + b1) on CUDA cores
-                const float x = xs[t * 128 + row];
+                const float2 x = splat2(xs[t * 128 + row]);
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
+                for (int i = 0; i < 16; i += 2) {
+                    const float2 o = ffma2(x, *reinterpret_cast<const float2*>(fp + 64 + c0 + i), *reinterpret_cast<const float2*>(fp + 96 + c0 + i));
+                    v[i] = fmaxf(o.x, 0.f);
+                    v[i + 1] = fmaxf(o.y, 0.f);
+                }
                 store_a_tmem16_f<kInt>(t_opnd + kTmO1 + (t & 3) * 32, v);
             };
             uint32_t it = 0, ny = 0, ny_slot = 0, ny_par = 1;      // empty-barrier parity of the previous use
@@ -1289,9 +1295,14 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                     }
                     if (h2) {
                         relu_bias(r2, 5, v);                                                     // b3
-                        const float x = xs[t2 * 128 + row];
+                        const float2 x = splat2(xs[t2 * 128 + row]);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
+                        for (int i = 0; i < 16; i += 2) {                                         // + shortcut
+                            const float2 sc = ffma2(x, *reinterpret_cast<const float2*>(fp + c0 + i), *reinterpret_cast<const float2*>(fp + 32 + c0 + i));
+                            const float2 o = fadd2(make_float2(v[i], v[i + 1]), sc);
+                            v[i] = fmaxf(o.x, 0.f);
+                            v[i + 1] = fmaxf(o.y, 0.f);
+                        }
                         if (ny >= 3) mbar_wait(&bar_y0_empty[ny_slot], ny_par);
                         tc_fence_after_sync();
                         store_a_tmem16_f<kInt>(t_opnd + kTmY0 + ny_slot * 32, v);
@@ -1341,7 +1352,11 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                         relu_bias(r5, 9, v);                                                     // b7
                         const float* sc = sc_mine + (t5 & 3) * 4096;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + sc[i * 128], 0.f);     // + (sc1 + b4)
+                        for (int i = 0; i < 16; i += 2) {                                         // + (sc1 + b4)
+                            const float2 o = fadd2(make_float2(v[i], v[i + 1]), make_float2(sc[i * 128], sc[(i + 1) * 128]));
+                            v[i] = fmaxf(o.x, 0.f);
+                            v[i + 1] = fmaxf(o.y, 0.f);
+                        }
                         store_a_row16_f<FMT>(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
                     }
                 }

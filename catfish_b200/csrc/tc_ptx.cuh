@@ -257,24 +257,6 @@ __device__ __forceinline__ void tmem_st8_u32(uint32_t taddr, const uint32_t* v) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ---------------------------------------------------------------- split bf16 ("bf16x3")
-// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi); a product a*b is evaluated as
-// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation (error ~2^-16 relative).
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-// Pack two floats' hi parts and lo parts into bf16x2 words (element 0 in the low half).
-// Uses the packed conversion (F2FP, FMA/ALU pipes) - the scalar F2F.BF16 runs on the XU pipe,
-// which the GRU epilogue needs for its transcendentals.
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // ---------------------------------------------------------------- packed fp32 pairs (FFMA2 / FADD2 / FMUL2)
 // sm_100 executes two fp32 operations per lane in one instruction: half the issue slots for the
 // epilogues' elementwise math (they are bound by instruction issue, not by the FMA pipe).
@@ -304,6 +286,25 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     return unpack2(d);
 }
 __device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+
+// ---------------------------------------------------------------- split bf16 ("bf16x3")
+// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi); a product a*b is evaluated as
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation (error ~2^-16 relative).
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// Pack two floats' hi parts and lo parts into bf16x2 words (element 0 in the low half).
+// Uses the packed conversion (F2FP, FMA/ALU pipes) - the scalar F2F.BF16 runs on the XU pipe,
+// which the GRU epilogue needs for its transcendentals.
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 r = ffma2(make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), splat2(-1.f),
+                           make_float2(x0, x1));                          // x - hi, both at once
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // ---------------------------------------------------------------- fp16 + e5m2 corrections ("f16e5")
 // x = h + l with h = fp16(x) (11 significant bits) and l the exact remainder.  A product a*w is
