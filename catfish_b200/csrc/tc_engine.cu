@@ -6,14 +6,14 @@
 // with split operands and fp32 accumulation in TMEM, in one of two formats:
 //   bf16x3  a_hi w_hi + a_lo w_hi + a_hi w_lo, three kind::f16 MMAs per K = 16 chunk
 //   f16e5   fp16 product + one e5m2 MMA over [a_l S | a_h / S] [w_h / S ; w_l S]: two
-//           pass-equivalents (default for the fused GRU layers of ResNetRNN; tc_ptx.cuh)
+//           pass-equivalents (default for the 128-wide fused GRU layers of ResNetRNN; tc_ptx.cuh)
 //
 // Default path of a pass (at most kTcChunkTiles tiles):
 //   TK2   tc_conv4_kernel        residual conv stack, two chains, operands in tensor memory
 //   TK4G  tc_gru_fused2_kernel   one GRU layer (input projection + recurrence), two tiles per CTA
 //   TK5   tc_head_kernel         dense 128 -> 1 + sigmoid from the partial dots of the last layer
-// preceded once per call by tc_range_flag_kernel (f16e5 only: fall back to the bf16x3 twins when the
-// input leaves fp16's safe range).  Cross-checks / other shapes: tc_conv_kernel, tc_conv2_kernel,
+// (the conv stack and the GRU layer it feeds use bf16x3, the 128-wide GRU layers f16e5).
+// Cross-checks / other shapes: tc_conv_kernel, tc_conv2_kernel,
 // tc_conv3_kernel (CF_TC_CONV=1..3), tc_gru_fused_kernel (CF_TC_FUSED=1), and the unfused pair
 //   TK3   tc_xproj_kernel  GRU input projection  xp = y W_x + b   (rnn_class.py:146,170: the
 //         x rows of gates/kernel and candidate/kernel, hoisted out of the time loop)
@@ -40,7 +40,7 @@ using namespace ptx;
 constexpr int kH = 64;            // GRU units
 constexpr int kC = 32;            // conv channels
 constexpr int kNX = 3 * kH;       // 192 projection columns per direction (r | u | c)
-constexpr int kTcChunkTiles = 1184;  // tiles per internal pass (8 tiles per chain of the GRU kernel)
+constexpr int kTcChunkTiles = 2368;  // tiles per internal pass (16 tiles per CTA of the GRU kernel; 1184: -1.4 %, 4736: -1.5 %)
 constexpr float kGateScale = -1.4426950408889634f;    // -log2(e)
 constexpr float kCandScale = 2.8853900817779268f;     // 2 log2(e)
 
@@ -106,15 +106,13 @@ struct TcLayer {
     float* bx = nullptr;              // [384]
     __nv_bfloat16* wh = nullptr;      // [dir]{Wg hi, Wg lo [8][128][8]; Wc hi, Wc lo [8][64][8]}
     uint8_t* wfused = nullptr;        // [dir]{Wgx, Wcx, Wgh, Wch} as in GruFusedCfg (in = 32 or 128), exponent domain
-    uint8_t* wfused_bf = nullptr;     // bf16x3 twin when wfused is f16e5
+    int fmt = 0;                      // operand format of wfused / of this layer's x and state operands
     float* bz = nullptr;              // [384] biases in the exponent domain
 };
 
 struct TcEngine {
     SimtEngine* simt = nullptr;       // fp32 conv stack for shapes TK2 is not specialised for
     uint8_t* conv_params = nullptr;   // TK2 parameter block (see ConvParams), nullptr = use simt
-    uint8_t* conv_params_bf = nullptr;  // the same in bf16x3 when conv_params is f16e5 (out-of-range fallback)
-    int* fmt_flag = nullptr;          // device flag: 1 = this call's input is outside the fp16 format's safe range
     int conv_nres = 0;
     std::vector<TcLayer> layers;
     float* head_w = nullptr;          // [128]
@@ -130,8 +128,9 @@ struct TcEngine {
     int x_depth = 0;                  // x blocks prefetched into L2 ahead of the ring (CF_TC_XDEPTH); measured: no gain, extra DRAM reads
     int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
-    int fmt = kFmtBf16x3;             // operand format of the default kernels (kFmtF16E5 unless CF_TC_FMT=0 or a cross-check
-                                      // variant / a network the default kernels do not cover is selected)
+    int fmt = kFmtBf16x3;             // operand format of the 128-wide fused GRU layers (kFmtF16E5 unless CF_TC_FMT=0 or a
+                                      // cross-check variant / a network the default kernels do not cover is selected); the
+                                      // conv stack and the first GRU layer (input = conv output) always run bf16x3
 };
 
 bool tc_supported(const HostModel& hm) {
@@ -169,10 +168,6 @@ TcEngine* tc_create(const HostModel& hm) {
                              e->conv_variant == 4 && e->fused_variant == 2 && e->use_fused;
         const char* env = getenv("CF_TC_FMT");
         e->fmt = covered && !(env && env[0] == '0') ? kFmtF16E5 : kFmtBf16x3;
-        if (e->fmt == kFmtF16E5) {
-            if (cudaMalloc(&e->fmt_flag, sizeof(int)) != cudaSuccess) e->fmt = kFmtBf16x3;
-            else e->owned.push_back(e->fmt_flag);
-        }
     }
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then the B operands in the given format (see ConvParams)
@@ -227,8 +222,7 @@ TcEngine* tc_create(const HostModel& hm) {
         }
         return blk;
         };
-        e->conv_params = tc_upload(e, build_conv_block(kFmtBf16x3));    // the conv stack is bf16x3 inside for both formats
-        e->conv_params_bf = e->conv_params;
+        e->conv_params = tc_upload(e, build_conv_block(kFmtBf16x3));    // the conv stack is bf16x3 throughout
         e->conv_nres = hm.n_res();
     }
     for (int l = 0; l < hm.n_rnn(); ++l) {
@@ -274,8 +268,11 @@ TcEngine* tc_create(const HostModel& hm) {
                 }
                 return wf;
             };
-            L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, build_fused(e->fmt)));
-            if (e->fmt == kFmtF16E5) L.wfused_bf = reinterpret_cast<uint8_t*>(tc_upload(e, build_fused(kFmtBf16x3)));
+            // The layer fed by the conv stack stays bf16x3: it contributes nearly all of f16e5's extra error
+            // (emulation: 5.8e-5 of 6.1e-5; conv activations span 2^-10 .. 60 and would need an fp16 range
+            // guard) and its K = 32 input part is too small to gain from the cheaper passes.
+            L.fmt = L.in == kC ? kFmtBf16x3 : e->fmt;
+            L.wfused = reinterpret_cast<uint8_t*>(tc_upload(e, build_fused(L.fmt)));
             std::vector<float> bz(2 * kNX);
             for (int d = 0; d < 2; ++d)
                 for (int j = 0; j < kNX; ++j)
@@ -1114,13 +1111,11 @@ template <int FMT>
 __global__ void __launch_bounds__(576, 1)
 tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
                 const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
-                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out,
-                const int* __restrict__ fmt_flag) {
-    // FMT is the format of the OUTPUT (the first GRU layer's x operand); inside the stack every operand is
-    // split bf16 - the epilogue, not the tensor pipe, bounds this kernel and the bf16 split is the cheaper one.
-    // Two launches per pass when the engine runs f16e5: this one only if its format is the call's format.
+                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+    // FMT is the format of the OUTPUT (the first GRU layer's x operand; the engine uses bf16x3); inside the
+    // stack every operand is split bf16 - the epilogue, not the tensor pipe, bounds this kernel and the bf16
+    // split is the cheaper one.
     constexpr int kInt = kFmtBf16x3;
-    if (fmt_flag && ((*fmt_flag != 0) != (FMT == kFmtBf16x3))) return;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* prm = smem;
     uint8_t* o2 = smem + ConvParams::kBytes;
@@ -2066,13 +2061,12 @@ template <int KX> struct GruF2Cfg {
     static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarFull = 5, kBarEmpty = 5 + kStages;
 };
 
-template <int KX, int FMT>
+template <int KX, int FMT, int FMT_OUT>
 __global__ void __launch_bounds__(608, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
                      const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth,
-                     long long* __restrict__ trace, const int* __restrict__ fmt_flag) {
-    if (fmt_flag && ((*fmt_flag != 0) != (FMT == kFmtBf16x3))) return;
+                     long long* __restrict__ trace) {
     using Cfg = GruF2Cfg<KX>;
     // debug timeline (CF_TC_TRACE): block 0 records (tag, SM clock) pairs for steps 36..39 of each role
     int tr_n = 0;
@@ -2404,7 +2398,20 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 }
                 if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 55);
                 if (y_out) {
-                    // next layer's A operand: block {hi, lo} x [16][128][8], features dir*64 + j
+                    // next layer's A operand: block {plane 0, plane 1} x [16][128][8], features dir*64 + j,
+                    // in the NEXT layer's operand format (a second split when it differs from this layer's)
+                    if (FMT_OUT != FMT) {
+#ifndef CF_PRECISE_ACT
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            split4<FMT_OUT>(h2[i >> 1].x, h2[i >> 1].y, h2[(i >> 1) + 1].x, h2[(i >> 1) + 1].y, i & 15,
+                                            hi + (i >> 4) * 8, lo + (i >> 4) * 8);
+#else
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            split4<FMT_OUT>(h[i], h[i + 1], h[i + 2], h[i + 3], i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
+#endif
+                    }
                     __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 8;
 #pragma unroll
                     for (int kg = 0; kg < 4; ++kg) {
@@ -2505,40 +2512,24 @@ __global__ void tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const f
     probs[src[g] + t] = p;
 }
 
-// ====================================================================== input range check (f16e5)
-// One thread per window: does any normalised sample of this call leave the range in which the fp16
-// operand format is safe (kF16SafeInput)?  Real signals stay within a few tens of MADs; a call that
-// does not (or that carries NaN / inf windows) is run by the bf16x3 twins of the kernels instead.
-__global__ void tc_range_flag_kernel(const int16_t* __restrict__ raw, const double* __restrict__ stats,
-                                     const float* __restrict__ xwin, const int64_t* __restrict__ src,
-                                     const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
-                                     int64_t n_windows, float limit, int* __restrict__ flag) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool bad = false;
-    if (g < n_windows) {
-        const int nv = valid[g];
-        const int64_t s0 = src[g];
-        if (nv > 0 && raw) {
-            const int r = read[g];
-            const double shift = stats[2 * r], lim = (double)limit * stats[2 * r + 1];
-            for (int t = 0; t < nv; ++t) bad |= !(fabs((double)raw[s0 + t] - shift) <= lim);
-        } else if (nv > 0) {
-            for (int t = 0; t < nv; ++t) bad |= !(fabsf(xwin[s0 + t]) <= limit);
-        }
-    }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
-}
-
 // ====================================================================== forward
 int simt_conv_stack(SimtEngine* e, const HostModel& hm, const int16_t* raw, const double* stats, const float* xwin,
                     WindowTable tab, int64_t tile0, int64_t tiles, int64_t chunk_tiles, const float** feat,
                     cudaStream_t stream, Profiler* prof);
 
-static size_t tc_workspace_bytes(const HostModel& hm, int64_t tiles) {
+// The projection buffer (192 KB per block) is only needed by the unfused projection + recurrence pair.
+static bool tc_needs_xp(const TcEngine* e) {
+    if (!e->use_fused) return true;
+    for (const TcLayer& L : e->layers)
+        if (!L.wfused) return true;
+    return false;
+}
+
+static size_t tc_workspace_bytes(const TcEngine* e, int64_t tiles) {
     const size_t blocks = (size_t)tiles * kWindow;
     size_t b = 0;
     b += blocks * 128 * kC * 2 * 2;          // conv output as A operand (K = 32)
-    b += blocks * 2 * kNX * 128 * 4;         // xp
+    if (tc_needs_xp(e)) b += blocks * 2 * kNX * 128 * 4;   // xp
     b += 2 * blocks * 128 * 2 * kH * 2 * 2;  // y ping-pong (K = 128 operands)
     b += blocks * 8 * 128 * 4;               // head partials
     return b + 4096;
@@ -2553,27 +2544,26 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<128>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3Smem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
-        CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
     }
     const int64_t chunk = n_tiles < kTcChunkTiles ? n_tiles : kTcChunkTiles;
-    CF_TRY(e->ws.ensure(tc_workspace_bytes(hm, chunk)));
+    CF_TRY(e->ws.ensure(tc_workspace_bytes(e, chunk)));
     const size_t blocks_max = (size_t)chunk * kWindow;
     uint8_t* p = static_cast<uint8_t*>(e->ws.ptr);
     __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(p);
     p += blocks_max * 128 * kC * 2 * 2;
     float* xp = reinterpret_cast<float*>(p);
-    p += blocks_max * 2 * kNX * 128 * 4;
+    if (tc_needs_xp(e)) p += blocks_max * 2 * kNX * 128 * 4;
     __nv_bfloat16* ybuf[2];
     ybuf[0] = reinterpret_cast<__nv_bfloat16*>(p);
     p += blocks_max * 128 * 2 * kH * 2 * 2;
@@ -2582,14 +2572,6 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
     float* head_part = reinterpret_cast<float*>(p);
 
     const int n_layers = (int)e->layers.size();
-    if (e->fmt == kFmtF16E5) {
-        ProfScope ps(prof, KC_K1_TABLE, stream);
-        CF_CUDA(cudaMemsetAsync(e->fmt_flag, 0, sizeof(int), stream));
-        const int64_t n_windows = n_tiles * kTileWindows;
-        tc_range_flag_kernel<<<(unsigned)ceil_div(n_windows, (int64_t)256), 256, 0, stream>>>(
-            raw, raw ? stats : nullptr, xwin, tab.src, tab.valid, tab.read, n_windows, kF16SafeInput, e->fmt_flag);
-        CF_LAUNCHED();
-    }
     for (int64_t tile0 = 0; tile0 < n_tiles; tile0 += kTcChunkTiles) {
         const int64_t tiles = std::min<int64_t>(kTcChunkTiles, n_tiles - tile0);
         const int64_t blocks = tiles * kWindow;
@@ -2600,16 +2582,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             ProfScope ps(prof, KC_K2_CONV, stream);
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
             if (e->conv_variant == 4 && e->conv_nres == 2) {
-                if (e->fmt == kFmtF16E5) {
-                    tc_conv4_kernel<1><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0, e->fmt_flag);
-                    CF_LAUNCHED();
-                    tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params_bf, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0, e->fmt_flag);
-                } else {
-                    tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0, nullptr);
-                }
+                tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                     tab.read, tile0, (int)tiles, a0);
             } else if (e->conv_variant >= 3 && e->conv_nres == 2) {
                 tc_conv3_kernel<<<grid, 576, kConv3Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                   tab.read, tile0, (int)tiles, a0);
@@ -2655,25 +2629,21 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
                     const float* hw_l = last ? e->head_w : nullptr;
                     float* hp_l = last ? head_part : nullptr;
-                    const bool e5 = e->fmt == kFmtF16E5;
-                    const int* flag = e5 ? e->fmt_flag : nullptr;
-                    const uint8_t* w_bf = e5 ? L.wfused_bf : L.wfused;
+                    // operand format of this layer and of the layer that reads its output
+                    const int fmt_out = last ? L.fmt : e->layers[l + 1].fmt;
                     if (L.in == kC) {
-                        if (e5) {
-                            tc_gru_fused2_kernel<32, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr, flag);
-                            CF_LAUNCHED();
-                        }
-                        tc_gru_fused2_kernel<32, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                            w_bf, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr, flag);
+                        if (fmt_out == kFmtF16E5)
+                            tc_gru_fused2_kernel<32, 0, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
+                        else
+                            tc_gru_fused2_kernel<32, 0, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
+                    } else if (L.fmt == kFmtF16E5) {
+                        tc_gru_fused2_kernel<128, 1, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
                     } else {
-                        if (e5) {
-                            tc_gru_fused2_kernel<128, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev, flag);
-                            CF_LAUNCHED();
-                        }
-                        tc_gru_fused2_kernel<128, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            w_bf, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, e5 ? nullptr : trace_dev, flag);
+                        tc_gru_fused2_kernel<128, 0, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
                     }
                     CF_LAUNCHED();
                     if (trace_dev) {

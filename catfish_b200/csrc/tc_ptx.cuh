@@ -315,11 +315,10 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
 // absolute errors below 2^-19 |w|.  Two pass-equivalents instead of the three of bf16x3 (tools/precision_emulation.py:
 // max |dp| 5.6e-5 vs 2.1e-5).
 constexpr float kCorrScale = 64.f;
-// fp16 tops out at 65504 and the corrections need |a| >= 2^-8: the conv activations of real signals
-// (median 0.3, maximum ~60 for normalised samples within +-10) sit inside that window.  Calls whose
-// normalised input exceeds kF16SafeInput run the bf16x3 kernels instead (tc_range_flag_kernel); the
-// fp16 conversion saturates rather than produce infinities.
-constexpr float kF16SafeInput = 1000.f;
+// fp16 tops out at 65504 and the corrections need |a| >= 2^-8: the engine uses this format where the
+// activations are GRU states in (-1, 1) (the 128-wide layers); the layer fed by the conv stack, whose
+// activations span 2^-10 .. 60 (and 4.5e5 behind a full-scale spike), stays split bf16.  The fp16
+// conversion saturates rather than produce infinities.
 // Two values -> fp16x2 word (element 0 in the low half), e5m2x2 of the scaled remainders and
 // e5m2x2 of the down-scaled fp16 parts (element 0 in the low byte).
 __device__ __forceinline__ void split_f16e5x2(float x0, float x1, uint32_t& main, uint32_t& lo, uint32_t& hi) {

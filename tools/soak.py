@@ -35,7 +35,7 @@ if __name__ == "__main__":
     assert fast.resolved_engine == "tcgen05"
     rng = np.random.default_rng(77)
     cases = [reads_for_tiles(t, rng) for t in (1, 2, 3, 4, 73, 74, 75, 147, 148, 149, 150, 295, 296, 297, 591, 592, 593,
-                                               1183, 1184, 1185, 1186, 2368, 2369)]
+                                               1183, 1184, 1185, 1186, 2367, 2368, 2369, 2370)]
     for _ in range(n_random):
         n = int(rng.integers(1, 200))
         kind = rng.integers(0, 3)
