@@ -5,6 +5,9 @@
 
 nvcc cross-compiles without a GPU.  The .so is git-ignored but travels with the
 working tree (e.g. to the GPU box).
+
+Environment (A/B builds, see tools/ab_lib.sh): CF_LIB_OUT = output path, CF_OBJ_TAG = prefix of the
+object files, CF_EXTRA_DEFS = extra nvcc flags, CF_PRECISE_ACT = ex2/rcp activations instead of MUFU.TANH.
 """
 
 import os
