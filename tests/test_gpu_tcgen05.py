@@ -29,8 +29,9 @@ def test_xproj_gemm_matches_float64(k, n_blocks):
 
 
 def _f16e5_emulated(a, w, s=64.0):
-    import torch
     """Bit-level model of the fp16 + e5m2-correction product (tc_ptx.cuh, tools/precision_emulation.py)."""
+    import torch
+
     def rnd(x, dt):
         return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dt).to(torch.float32).numpy().astype(np.float64)
     ah, wh = rnd(a, torch.float16), rnd(w, torch.float16)
