@@ -13,7 +13,7 @@ Restates, in plain Python/numpy, the functions of
 Pinned: tests/test_oracle_vs_reference.py runs these against the reference's own
 functions imported unmodified (oracle/ref_infer.py) on seeded inputs, and
 tests/golden/ holds vectors generated from the reference functions by
-tools/make_golden.py.
+tests/tools/make_golden.py.
 
 The ``*_loops`` variants follow the reference statement by statement (small
 cases); the vectorised variants return identical results and are used for the

@@ -29,7 +29,7 @@ def test_xproj_gemm_matches_float64(k, n_blocks):
 
 
 def _f16e5_emulated(a, w, s=64.0):
-    """Bit-level model of the fp16 + e5m2-correction product (tc_ptx.cuh, tools/precision_emulation.py)."""
+    """Bit-level model of the fp16 + e5m2-correction product (tc_ptx.cuh, tests/tools/precision_emulation.py)."""
     import torch
 
     def rnd(x, dt):

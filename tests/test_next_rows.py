@@ -1,7 +1,7 @@
 """Validation counts (next row N4) and event voting (next row N3).
 
 CPU: the oracle restatements against vectors produced by the reference's own functions
-(tools/make_golden_next.py) and the host-side helpers.  GPU: the K9 / K10 kernels through the
+(tests/tools/make_golden_next.py) and the host-side helpers.  GPU: the K9 / K10 kernels through the
 C ABI against the oracle and the golden vectors."""
 import json
 import os

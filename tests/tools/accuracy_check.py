@@ -1,14 +1,14 @@
 #!/usr/bin/env python3
 """max / percentile |dp| of the GPU path against the fp32 CPU oracle on synthetic 10k-sample reads.
 
-    python tools/accuracy_check.py [n_reads]
+    python tests/tools/accuracy_check.py [n_reads]
 """
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from catfish_b200 import infer, neural_network, synth, weights
 from oracle import postprocess, tf_graph
 m = neural_network.load_network("ResNetRNN", None, 30000)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate the golden vectors under tests/golden/ (run in the build container).
 
-    python tools/make_golden.py
+    python tests/tools/make_golden.py
 
 Sources of truth:
 * pre/post-processing: the REFERENCE's own functions, imported unmodified from
@@ -19,7 +19,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT)
 from catfish_b200 import synth, weights  # noqa: E402
 from oracle import postprocess, ref_infer, tf_graph  # noqa: E402

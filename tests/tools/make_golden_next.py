@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate tests/golden/events.json and confusion.json ("next" rows N3 / N4; build container only).
 
-    python tools/make_golden_next.py
+    python tests/tools/make_golden_next.py
 
 Source of truth: the REFERENCE's own functions executed from /root/reference through
 oracle/ref_infer.py - ``correct_events`` (networks/correct_output.py:14-76, results recovered from
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT)
 from oracle import ref_infer  # noqa: E402
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Emulate tensor-core operand formats on the CPU graph: max |dp| against the fp64 graph.
 
-    python tools/precision_emulation.py [n_reads] [read_len]
+    python tests/tools/precision_emulation.py [n_reads] [read_len]
 
 Every 32 -> 32 convolution and every GRU matmul of the oracle graph (oracle/tf_graph.py) is replaced by
 a product of ROUNDED operands accumulated in fp64 (the tensor core accumulates in fp32; that
@@ -20,7 +20,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from catfish_b200 import synth, weights  # noqa: E402
 from oracle import postprocess, tf_graph  # noqa: E402
 

@@ -14,8 +14,8 @@ timeout 300 python tools/profile_workload.py 96 2 > gpurun_out/prof_workload.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_gru_fused2_kernel|tc_conv4_kernel' -s 8 -c 4 -f -o gpurun_out/prof_main \
     python tools/profile_workload.py 96 2 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
-timeout 300 python tools/accuracy_check.py > gpurun_out/accuracy.txt 2>&1; tail -1 gpurun_out/accuracy.txt
+timeout 300 python tests/tools/accuracy_check.py > gpurun_out/accuracy.txt 2>&1; tail -1 gpurun_out/accuracy.txt
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.txt 2>&1; tail -c 300 gpurun_out/bench_ref.txt
 timeout 600 python tools/tail_accuracy.py 12 256 > gpurun_out/tail_accuracy.txt 2>&1; tail -1 gpurun_out/tail_accuracy.txt
-timeout 300 python tools/accuracy_check.py 200 >> gpurun_out/accuracy.txt 2>&1; tail -1 gpurun_out/accuracy.txt
+timeout 300 python tests/tools/accuracy_check.py 200 >> gpurun_out/accuracy.txt 2>&1; tail -1 gpurun_out/accuracy.txt
 timeout 300 python tools/latency_long_reads.py 1 8 64 > gpurun_out/long_reads.txt 2>&1; tail -3 gpurun_out/long_reads.txt
