@@ -8,8 +8,9 @@ CPU restatement of
 Pinning: ``confusion_counts`` and ``vote_events`` are checked against the reference's own
 functions executed in the build container (oracle/ref_infer.py ``load_metrics`` /
 ``run_correct_events``; vectors committed under tests/golden/).  The loss / accuracy formulas
-are TensorFlow's published definitions (tf.nn.sigmoid_cross_entropy_with_logits, tf.round =
-round-half-even); TensorFlow itself is not installed, so that part is "parity unpinned".
+are pinned by the reference's shipped meta-graph: its ``accuracy/Mean`` and ``loss/Mean`` nodes
+executed by tests/tools/meta_graph_interp.py (golden ``val_*`` entries of
+tests/golden/forward_resnetrnn_shipped.npz; tests/test_oracle.py::test_validation_heads_against_golden).
 """
 
 import numpy as np

@@ -2,11 +2,18 @@
 import numpy as np
 import pytest
 
-from helpers import golden, hpm_from_golden, random_labels
+import os
+import sys
+
+from helpers import golden, hpm_from_golden, random_bn_weights, random_labels
 from catfish_b200 import synth, weights
-from oracle import postprocess, ref_infer, tf_graph
+from oracle import postprocess, ref_infer, tf_graph, validation
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+import meta_graph_interp as mgi  # noqa: E402
 
 needs_ref = pytest.mark.skipif(not ref_infer.available(), reason="reference tree not mounted")
+needs_meta = pytest.mark.skipif(not mgi.available(), reason="reference meta-graph not mounted")
 
 
 def test_postprocess_against_golden():
@@ -99,6 +106,72 @@ def test_forward_against_golden_shipped(shipped_weights):
         x, pad = postprocess.pad_and_window(postprocess.normalize_raw_signal(raw))
         p64 = tf_graph.forward_np(shipped_weights, x, np.float64)[:-pad]
         np.testing.assert_allclose(p64, g["read%d_p64" % i], rtol=0, atol=1e-12)
+
+
+def test_golden_sources_are_the_reference_graph():
+    """The probability goldens come from executing the reference's shipped meta-graph, not from the oracle."""
+    for name in ("forward_resnetrnn_shipped.npz", "forward_resnetrnn_randbn_seed14.npz",
+                 "forward_rnn_le64_ns3_seed11.npz", "forward_resnet_ls32_ns2_seed12.npz"):
+        assert str(golden(name)["source"]).startswith("meta_graph_interp")
+
+
+def test_forward_against_golden_random_bn():
+    """Seeded weights with non-trivial BN statistics through the reference graph (golden) vs the oracle."""
+    g = golden("forward_resnetrnn_randbn_seed14.npz")
+    w = random_bn_weights(int(g["seed"]))
+    np.testing.assert_allclose(tf_graph.forward_np(w, g["x"], np.float64), g["p64"], rtol=0, atol=1e-12)
+    assert np.abs(tf_graph.forward_torch(w, g["x"]) - g["p64"]).max() < 2e-6
+    assert np.abs(g["p32"] - g["p64"]).max() < 2e-6
+
+
+def test_validation_heads_against_golden(shipped_weights):
+    """accuracy/Mean and loss/Mean of the reference graph (rnn_class.py:73-88, 240-241) vs oracle.validation."""
+    g = golden("forward_resnetrnn_shipped.npz")
+    x, pad = postprocess.pad_and_window(postprocess.normalize_raw_signal(g["read0"]))
+    z = tf_graph.forward_np(shipped_weights, x, np.float64, return_logits=True)
+    _, acc, loss = validation.test_network(z, g["val_labels"], pad)
+    assert acc == float(g["val_acc64"])
+    assert abs(loss - float(g["val_loss64"])) < 1e-12
+    assert abs(acc - float(g["val_acc32"])) < 1e-6 and abs(loss - float(g["val_loss32"])) < 1e-6
+
+
+@needs_meta
+def test_oracle_equals_reference_meta_graph_live():
+    """Pin: oracle.tf_graph == the reference's ckpnt-30000.meta executed op by op, on 3 reads incl. a
+    35-divisible length (the extra-window padding case), fp64 to 1e-12 and torch-fp32 to 2e-6."""
+    ref_vars = mgi.load_reference_variables()
+    shipped = weights.load_shipped()
+    assert sorted(k for k in ref_vars if weights_is_inference(k)) == sorted(shipped)
+    tg = tf_graph.TorchGraph(shipped)
+    graph64 = mgi.MetaGraph(mgi.META, ref_vars, np.float64)
+    assert graph64.tf_version == "1.10.0" and len(graph64.subgraph(mgi.PREDICTIONS)) == 1049
+    for n, seed in ((350, 1), (613, 2), (1999, 3)):
+        raw = synth.synth_read(n, seed)
+        x, pad = postprocess.pad_and_window(postprocess.normalize_raw_signal(raw))
+        p64, _ = mgi.predictions(x, graph=graph64)
+        assert set(graph64.iterations.values()) == {35} and len(graph64.iterations) == 6
+        np.testing.assert_allclose(tf_graph.forward_np(shipped, x, np.float64), p64, rtol=0, atol=1e-12)
+        assert np.abs(tg.infer(x) - p64).max() < 2e-6
+    p32, g32 = mgi.predictions(x, np.float32, variables=ref_vars, seed=5)
+    assert np.abs(p32 - p64).max() < 2e-6
+    assert len(g32.executed) == 44                                      # every op type of the sub-graph ran
+    # dropout mask at keep_prob 1.0 is the identity whatever the random draw (rnn_class.py:151-154, 217)
+    np.testing.assert_array_equal(mgi.predictions(x, np.float32, variables=ref_vars, seed=6)[0], p32)
+
+
+@needs_meta
+@pytest.mark.parametrize("kind,hpm", [("RNN", dict(layer_size=64, n_layers=3)),
+                                      ("ResNet", dict(layer_size_res=32, n_layers_res=2))])
+def test_variants_equal_rewired_reference_sub_graphs(kind, hpm):
+    w = weights.random_init(kind, seed=21, **hpm)
+    x = np.random.default_rng(3).normal(0, 1.5, size=(6, 35, 1)).astype(np.float32)
+    np.testing.assert_allclose(tf_graph.forward_np(w, x, np.float64), mgi.predictions_variant(kind, x, w),
+                               rtol=0, atol=1e-12)
+
+
+def weights_is_inference(name):
+    from catfish_b200 import tf_checkpoint
+    return tf_checkpoint.is_inference_tensor(name)
 
 
 @pytest.mark.parametrize("name", ["forward_rnn_le64_ns3_seed11.npz", "forward_resnet_ls32_ns2_seed12.npz",

@@ -7,9 +7,13 @@ Sources of truth:
 * pre/post-processing: the REFERENCE's own functions, imported unmodified from
   /root/reference/catfish/infer.py (oracle/ref_infer.py) - normalize_raw_signal,
   class_from_threshold, correct_short, hp_in_pred;
-* network probabilities: the oracle's float64 numpy restatement of the TF graph
-  (oracle/tf_graph.py) on the shipped checkpoint / seeded random-init weights
-  (TensorFlow itself cannot run here).
+* network probabilities: the REFERENCE's own op graph, the shipped
+  catfish/ResNetRNN/checkpoints/ckpnt-30000.meta, executed node by node by
+  tests/tools/meta_graph_interp.py (fp64 and fp32) with the shipped bundle's weights,
+  with seeded random weights incl. non-trivial BN statistics, and - for the RNN-only /
+  ResNet-only variants - with the graph's own sub-graphs rewired as the reference's
+  variants wire them.  Only the H = 16 RNN vector comes from the oracle restatement
+  (the graph's consts carry H = 64); its ``source`` entry says so.
 
 The vectors are small (a few hundred KB) so the GPU box, which has no reference
 tree, can check both the oracle and the CUDA path against them.
@@ -23,6 +27,10 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT)
 from catfish_b200 import synth, weights  # noqa: E402
 from oracle import postprocess, ref_infer, tf_graph  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
+import meta_graph_interp as mgi  # noqa: E402
+from helpers import random_bn_weights  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -84,19 +92,37 @@ def main():
     lengths = [700, 1225, 1999, 2000]        # 1225 = 35 * 35: the "extra window" padding case
     reads = synth.synth_reads(lengths, base_seed=4242)
     torch_graph = tf_graph.TorchGraph(w)
+    ref_vars = mgi.load_reference_variables()          # straight from the reference's .index/.data bundle
     fw["n_reads"] = np.array(len(reads))
+    fw["source"] = np.array("meta_graph_interp: ckpnt-30000.meta executed op by op")
     for i, r in enumerate(reads):
         norm = ref.normalize_raw_signal(r, "median")
         x, pad = postprocess.pad_and_window(norm)
-        p64 = tf_graph.forward_np(w, x, np.float64)[:-pad]
-        p32 = torch_graph.infer(x)[:-pad]
+        p64 = mgi.predictions(x, np.float64, variables=ref_vars)[0][:-pad]
+        p32 = mgi.predictions(x, np.float32, variables=ref_vars)[0][:-pad]
         labels = ref.correct_short(ref.class_from_threshold(p32))
         hps = ref.hp_in_pred(labels)
         fw["read%d" % i] = r
         fw["read%d_p64" % i] = p64
         fw["read%d_p32" % i] = p32.astype(np.float32)
         fw["read%d_hps" % i] = np.array(hps, np.int64).reshape(-1, 2)
+    # validation heads of the same graph (rnn_class.py:240-241): accuracy/Mean, loss/Mean on read 0
+    x, pad = postprocess.pad_and_window(ref.normalize_raw_signal(reads[0], "median"))
+    y = (np.random.default_rng(77).random(x.shape) < 0.3).astype(np.float32)
+    fw["val_labels"] = y.reshape(-1).astype(np.int8)
+    for tag, dt in (("64", np.float64), ("32", np.float32)):
+        acc, loss, _ = mgi.accuracy_loss(x, y, dt, variables=ref_vars)
+        fw["val_acc" + tag], fw["val_loss" + tag] = np.array(acc), np.array(loss)
     np.savez_compressed(os.path.join(OUT, "forward_resnetrnn_shipped.npz"), **fw)
+
+    # ---- the same graph with seeded random weights and NON-trivial BN statistics (the shipped bundle has
+    # moving_mean = 0, moving_variance = 1, which would hide an error in the BN arithmetic)
+    wb = random_bn_weights(14)
+    x = rng.normal(0, 1.5, size=(24, 35, 1)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "forward_resnetrnn_randbn_seed14.npz"), x=x, seed=np.array(14),
+                        p64=mgi.predictions(x, np.float64, variables=wb)[0],
+                        p32=mgi.predictions(x, np.float32, variables=wb)[0].astype(np.float32),
+                        source=np.array("meta_graph_interp"))
 
     # ---- forward vectors: random-init RNN-only and ResNet-only (A14), 48 windows
     for kind, hpm, seed in (("RNN", dict(layer_size=64, n_layers=3), 11),
@@ -104,10 +130,13 @@ def main():
                             ("RNN", dict(layer_size=16, n_layers=2), 13)):
         wr = weights.random_init(kind, seed=seed, **hpm)
         x = rng.normal(0, 1.5, size=(48, 35, 1)).astype(np.float32)
-        p64 = tf_graph.forward_np(wr, x, np.float64)
+        if hpm.get("layer_size", 64) == 64:
+            p64, source = mgi.predictions_variant(kind, x, wr, np.float64), "meta_graph_interp (sub-graphs rewired)"
+        else:
+            p64, source = tf_graph.forward_np(wr, x, np.float64), "oracle/tf_graph.py (graph consts carry H = 64)"
         tag = "%s_%s" % (kind.lower(), "_".join("%s%d" % (k[0] + k[-1], v) for k, v in sorted(hpm.items())))
         np.savez_compressed(os.path.join(OUT, "forward_%s_seed%d.npz" % (tag, seed)),
-                            x=x, p64=p64, seed=np.array(seed), kind=np.array(kind),
+                            x=x, p64=p64, seed=np.array(seed), kind=np.array(kind), source=np.array(source),
                             **{"hpm_" + k: np.array(v) for k, v in hpm.items()})
     # ---- chunk merging (next row N1): execute the reference CLI's own source lines (catfish/catfish:58-81, 121-135)
     import copy
