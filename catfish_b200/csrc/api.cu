@@ -256,12 +256,21 @@ struct cf_model {
     // host-buffer entry point
     cf::DevBuf h_raw, h_intervals, h_ioff, h_probs;
     cf::HostBuf pin_io;
+    cudaEvent_t last_done = nullptr; // end of the previous asynchronous call on this handle (handle_begin / handle_end)
     std::mutex mu;
 };
 
 namespace cf {
 
 constexpr int kWideSlots = 64;
+
+// Select `device` for the duration of a C-ABI call and restore the caller's current device on return
+// (a multi-GPU process must not find its current device changed by creating, using or destroying a model).
+struct DeviceGuard {
+    int prev = -1;
+    int set(int device);
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static int use_device(int device) {
     int n = 0;
@@ -280,12 +289,36 @@ static int use_device(int device) {
     return CF_OK;
 }
 
+int DeviceGuard::set(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
+    CF_TRY(use_device(device));
+    if (cur >= 0 && cur != device) prev = cur;
+    return CF_OK;
+}
+
+// One handle = one set of scratch buffers: a call on stream B must not start while the previous call's
+// kernels (possibly on stream A) still use them.  Every asynchronous entry point waits on the event of the
+// previous call first (a no-op on the same stream) and records it again when its own work is enqueued.
+static int handle_begin(cf_model* m, cudaStream_t st);
+static int handle_end(cf_model* m, cudaStream_t st);
+
 static int engine_forward(cf_model* m, const int16_t* raw, const double* stats, const float* xwin,
                           WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream,
                           bool want_logits = false) {
     if (m->engine == CF_ENGINE_TCGEN05)
         return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits);
     return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits);
+}
+
+static int handle_begin(cf_model* m, cudaStream_t st) {
+    if (m->last_done) CF_CUDA(cudaStreamWaitEvent(st, m->last_done, 0));
+    return CF_OK;
+}
+static int handle_end(cf_model* m, cudaStream_t st) {
+    if (!m->last_done) CF_CUDA(cudaEventCreateWithFlags(&m->last_done, cudaEventDisableTiming));
+    CF_CUDA(cudaEventRecord(m->last_done, st));
+    return CF_OK;
 }
 
 // Validate offsets and lay out the windows of every read (infer.py:32-43).
@@ -490,7 +523,8 @@ int cf_merge_chunks(int32_t device, const int64_t* intervals_dev, const int64_t*
         return CF_ERR_BAD_ARG;
     }
     if (n_reads == 0) return CF_OK;
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t n_int = interval_offsets_host[n_reads] - interval_offsets_host[0];
     if (n_int < 0 || (n_int > 0 && !intervals_dev)) { cf::set_error("cf_merge_chunks: bad offsets"); return CF_ERR_BAD_ARG; }
@@ -522,7 +556,8 @@ int cf_split_raw(int32_t device, const int16_t* raw_dev, const int64_t* offsets_
         cf::set_error("cf_split_raw: bad argument");
         return CF_ERR_BAD_ARG;
     }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TempBufs tmp;
     cf::DevBuf* off = tmp.make();
@@ -539,14 +574,16 @@ int cf_split_raw(int32_t device, const int16_t* raw_dev, const int64_t* offsets_
 int cf_selftest_xproj(int32_t device, const float* a_dev, int64_t n_blocks, int32_t k, const float* wx_host,
                       const float* bias_host, float* out_dev, void* stream) {
     if (!a_dev || !wx_host || !bias_host || !out_dev || n_blocks <= 0) { cf::set_error("cf_selftest_xproj: bad argument"); return CF_ERR_BAD_ARG; }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     return cf::tc_selftest_xproj(a_dev, n_blocks, k, wx_host, bias_host, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int cf_selftest_f16e5(int32_t device, const float* a_dev, int32_t k, int32_t n, const float* w_host, int32_t mode,
                       float* out_dev, void* stream) {
     if (!a_dev || !w_host || !out_dev) { cf::set_error("cf_selftest_f16e5: bad argument"); return CF_ERR_BAD_ARG; }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     return cf::tc_selftest_f16e5(a_dev, k, n, w_host, mode, out_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -582,7 +619,8 @@ int cf_model_create(const cf_model_desc* desc, const float* const* tensors, cons
             return CF_ERR_BAD_ARG;
         }
     }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cf_model* m = new cf_model();
     m->device = device;
     cf::build_host_model(*desc, tensors, &m->hm);
@@ -608,13 +646,15 @@ int cf_model_create(const cf_model_desc* desc, const float* const* tensors, cons
 
 void cf_model_destroy(cf_model* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    cf::DeviceGuard guard;
+    if (guard.set(m->device) != CF_OK) cudaSetDevice(m->device);
     cudaDeviceSynchronize();
     cf::simt_destroy(m->simt);
     cf::tc_destroy(m->tc);
     m->pin_plan.release(); m->plan_dev.release(); m->stats.release(); m->wide_flags.release();
     m->wide_scratch.release(); m->k1_chunked.release(); m->k1_chunk_tab.release(); m->tab_src.release(); m->tab_valid.release(); m->tab_read.release();
     m->probs_internal.release();
+    m->val_logits.release(); m->val_partial.release();
     m->k6.bits.release(); m->k6.block_cnt.release(); m->k6.read_cnt.release(); m->k6.misc.release();
     m->h_raw.release(); m->h_intervals.release(); m->h_ioff.release(); m->h_probs.release();
     m->pin_io.release();
@@ -622,6 +662,7 @@ void cf_model_destroy(cf_model* m) {
     if (m->plan_copied) cudaEventDestroy(m->plan_copied);
     m->pin_chunks.release();
     if (m->chunks_copied) cudaEventDestroy(m->chunks_copied);
+    if (m->last_done) cudaEventDestroy(m->last_done);
     delete m;
 }
 
@@ -634,7 +675,8 @@ int cf_model_operand_format(const cf_model* m) {
 int cf_profile_enable(cf_model* m, int32_t on) {
     if (!m) { cf::set_error("cf_profile_enable: NULL model"); return CF_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> lock(m->mu);
-    cudaSetDevice(m->device);
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
     m->prof.reset();
     m->prof.on = on != 0;
     return CF_OK;
@@ -646,7 +688,8 @@ const char* cf_profile_class_name(int32_t cls) { return cf::kernel_class_name(cl
 int cf_profile_read(cf_model* m, double* ms_out, int64_t* launches_out, int32_t n) {
     if (!m || !ms_out || !launches_out || n < cf::KC_COUNT) { cf::set_error("cf_profile_read: bad argument"); return CF_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> lock(m->mu);
-    cudaSetDevice(m->device);
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
     m->prof.collect();
     for (int i = 0; i < cf::KC_COUNT; ++i) { ms_out[i] = m->prof.ms[i]; launches_out[i] = m->prof.launches[i]; }
     return CF_OK;
@@ -655,7 +698,8 @@ int cf_profile_read(cf_model* m, double* ms_out, int64_t* launches_out, int32_t 
 int cf_model_reserve(cf_model* m, int64_t max_samples, int32_t max_reads) {
     if (!m || max_samples < 0 || max_reads < 0) { cf::set_error("cf_model_reserve: bad argument"); return CF_ERR_BAD_ARG; }
     std::lock_guard<std::mutex> lock(m->mu);
-    CF_TRY(cf::use_device(m->device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
     const int64_t windows = max_samples / cf::kWindow + max_reads;
     const int64_t tiles = cf::ceil_div(windows, cf::kTileWindows);
     cf::WindowTable tab;
@@ -675,15 +719,19 @@ int cf_infer_windows(cf_model* m, const float* x_dev, int64_t n_windows, float* 
     }
     if (n_windows == 0) return CF_OK;
     std::lock_guard<std::mutex> lock(m->mu);
-    CF_TRY(cf::use_device(m->device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t tiles = cf::ceil_div(n_windows, cf::kTileWindows);
     cf::WindowTable tab;
     CF_TRY(cf::ensure_table(m, tiles, &tab));
     const int64_t slots = tiles * cf::kTileWindows;
+    CF_TRY(cf::handle_begin(m, st));
     cf::dense_window_table_kernel<<<(unsigned)cf::ceil_div(slots, 256), 256, 0, st>>>(n_windows, slots, tab.src, tab.valid, tab.read);
     CF_LAUNCHED();
-    return cf::engine_forward(m, nullptr, nullptr, x_dev, tab, tiles, probs_dev, st);
+    const int rc = cf::engine_forward(m, nullptr, nullptr, x_dev, tab, tiles, probs_dev, st);
+    CF_TRY(cf::handle_end(m, st));
+    return rc;
 }
 
 int cf_validate_windows(cf_model* m, const float* x_dev, const uint8_t* labels_dev, int64_t n_windows,
@@ -694,7 +742,8 @@ int cf_validate_windows(cf_model* m, const float* x_dev, const uint8_t* labels_d
         return CF_ERR_BAD_ARG;
     }
     std::lock_guard<std::mutex> lock(m->mu);
-    CF_TRY(cf::use_device(m->device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t n = n_windows * cf::kWindow;
     const int64_t tiles = cf::ceil_div(n_windows, cf::kTileWindows);
@@ -704,6 +753,7 @@ int cf_validate_windows(cf_model* m, const float* x_dev, const uint8_t* labels_d
     cf::WindowTable tab;
     CF_TRY(cf::ensure_table(m, tiles, &tab));
     const int64_t slots = tiles * cf::kTileWindows;
+    CF_TRY(cf::handle_begin(m, st));
     cf::dense_window_table_kernel<<<(unsigned)cf::ceil_div(slots, 256), 256, 0, st>>>(n_windows, slots, tab.src, tab.valid, tab.read);
     CF_LAUNCHED();
     CF_TRY(cf::engine_forward(m, nullptr, nullptr, x_dev, tab, tiles, m->val_logits.as<float>(), st, /*want_logits=*/true));
@@ -713,6 +763,7 @@ int cf_validate_windows(cf_model* m, const float* x_dev, const uint8_t* labels_d
     long long host[6];
     CF_CUDA(cudaMemcpyAsync(host, result, sizeof(host), cudaMemcpyDeviceToHost, st));
     CF_CUDA(cudaStreamSynchronize(st));
+    CF_TRY(cf::handle_end(m, st));
     counts_out[0] = host[0];
     counts_out[1] = host[1];
     counts_out[2] = host[2] - padding_size;      // rnn_class.py:247
@@ -752,7 +803,8 @@ int cf_vote_events(int32_t device, const double* scores_dev, int64_t n_scores, c
     if (empty_event_out) *empty_event_out = 0;
     if (n_voted == 0) return CF_OK;
     if (!classes_dev) { cf::set_error("cf_vote_events: classes_dev is NULL"); return CF_ERR_BAD_ARG; }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TempBufs tmp;
     cf::DevBuf* ev = tmp.make();
@@ -779,10 +831,14 @@ int cf_infer_reads(cf_model* m, const int16_t* raw_dev, const int64_t* offsets_h
         return CF_ERR_BAD_ARG;
     }
     std::lock_guard<std::mutex> lock(m->mu);
-    CF_TRY(cf::use_device(m->device));
-    return cf::infer_reads_device(m, raw_dev, offsets_host, n_reads, probs_dev, intervals_dev,
-                                  interval_offsets_dev, capacity, threshold, min_run, ext_left,
-                                  ext_right, static_cast<cudaStream_t>(stream));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CF_TRY(cf::handle_begin(m, st));
+    const int rc = cf::infer_reads_device(m, raw_dev, offsets_host, n_reads, probs_dev, intervals_dev,
+                                          interval_offsets_dev, capacity, threshold, min_run, ext_left, ext_right, st);
+    CF_TRY(cf::handle_end(m, st));
+    return rc;
 }
 
 int64_t cf_max_intervals(int64_t total_samples, int32_t n_reads, int32_t min_run) {
@@ -802,7 +858,8 @@ int cf_infer_reads_host(cf_model* m, const int16_t* raw_host, const int64_t* off
         return CF_ERR_BAD_ARG;
     }
     std::lock_guard<std::mutex> lock(m->mu);
-    CF_TRY(cf::use_device(m->device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t base = n_reads > 0 ? offsets_host[0] : 0;
     const int64_t total = n_reads > 0 ? offsets_host[n_reads] - base : 0;
@@ -822,6 +879,7 @@ int cf_infer_reads_host(cf_model* m, const int16_t* raw_host, const int64_t* off
         cf::BatchPlan whole;                       // reject bad / empty reads before any asynchronous copy reads the caller's buffer
         CF_TRY(cf::make_plan(off.data(), n_reads, &whole));
     }
+    CF_TRY(cf::handle_begin(m, st));
     // (Cutting the batch into groups of whole passes whose copies overlap the previous group's kernels was
     // measured: no gain - the copy is 1.2-1.5 ms of a 75 ms step and the extra K1 / K6 sequences cost as much.)
     if (total > 0)
@@ -841,6 +899,7 @@ int cf_infer_reads_host(cf_model* m, const int16_t* raw_host, const int64_t* off
     if (probs_host && total > 0)
         CF_CUDA(cudaMemcpyAsync(probs_host, probs_dev, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, st));
     CF_CUDA(cudaStreamSynchronize(st));
+    CF_TRY(cf::handle_end(m, st));
     if (found > capacity) {
         cf::set_error("cf_infer_reads_host: %lld intervals found, capacity %lld", (long long)found, (long long)capacity);
         return CF_ERR_CAPACITY;
@@ -856,7 +915,8 @@ int cf_normalize_reads(int32_t device, const int16_t* raw_dev, const int64_t* of
         return CF_ERR_BAD_ARG;
     }
     if (n_reads == 0) return CF_OK;
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int32_t r = 0; r < n_reads; ++r)
         if (offsets_host[r + 1] < offsets_host[r]) { cf::set_error("cf_normalize_reads: offsets decrease"); return CF_ERR_BAD_ARG; }
@@ -890,7 +950,8 @@ int cf_call_intervals(int32_t device, const void* probs_dev, int32_t probs_is_f6
         cf::set_error("cf_call_intervals: bad argument");
         return CF_ERR_BAD_ARG;
     }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_reads == 0) {
         CF_CUDA(cudaMemsetAsync(interval_offsets_dev, 0, sizeof(int64_t), st));
@@ -916,7 +977,8 @@ int cf_call_intervals(int32_t device, const void* probs_dev, int32_t probs_is_f6
 int cf_class_from_threshold(int32_t device, const double* scores_dev, int64_t n, double threshold,
                             int64_t* labels_dev, void* stream) {
     if (n < 0 || (n > 0 && (!scores_dev || !labels_dev))) { cf::set_error("cf_class_from_threshold: bad argument"); return CF_ERR_BAD_ARG; }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     return cf::k6_class_from_threshold(scores_dev, n, threshold, labels_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -926,7 +988,8 @@ int cf_correct_short(int32_t device, const int64_t* labels_dev, int64_t n, int32
         cf::set_error("cf_correct_short: bad argument");
         return CF_ERR_BAD_ARG;
     }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     return cf::k6_correct_short(labels_dev, n, threshold, out_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -937,7 +1000,8 @@ int cf_hp_in_pred(int32_t device, const int64_t* labels_dev, int64_t n, int32_t 
         return CF_ERR_BAD_ARG;
     }
     if (n == 0) { cf::set_error("cf_hp_in_pred: empty input (the reference raises IndexError, infer.py:151)"); return CF_ERR_EMPTY_READ; }
-    CF_TRY(cf::use_device(device));
+    cf::DeviceGuard guard;
+    CF_TRY(guard.set(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TempBufs tmp;
     cf::DevBuf* off = tmp.make();

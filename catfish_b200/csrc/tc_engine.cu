@@ -13,8 +13,7 @@
 //   TK4G  tc_gru_fused2_kernel   one GRU layer (input projection + recurrence), two tiles per CTA
 //   TK5   tc_head_kernel         dense 128 -> 1 + sigmoid from the partial dots of the last layer
 // (the conv stack and the GRU layer it feeds use bf16x3, the 128-wide GRU layers f16e5).
-// Cross-checks / other shapes: tc_conv_kernel, tc_conv2_kernel,
-// tc_conv3_kernel (CF_TC_CONV=1..3), tc_gru_fused_kernel (CF_TC_FUSED=1), and the unfused pair
+// Other shapes / cross-checks: tc_conv2_kernel (networks with ONE residual block), and the unfused pair
 //   TK3   tc_xproj_kernel  GRU input projection  xp = y W_x + b   (rnn_class.py:146,170: the
 //         x rows of gates/kernel and candidate/kernel, hoisted out of the time loop)
 //   TK4   tc_gru_kernel    GRU recurrence over the 35 steps of a window tile, both directions
@@ -45,6 +44,14 @@ constexpr float kGateScale = -1.4426950408889634f;    // -log2(e)
 constexpr float kCandScale = 2.8853900817779268f;     // 2 log2(e)
 
 constexpr int kFmtBf16x3 = 0, kFmtF16E5 = 1;   // operand formats, see "operand formats" below
+
+// Sensitivity experiments on TK4G, BUILD-TIME ONLY (-DCF_EXP=<bits>, tools/ab_exp.sh builds variant libraries;
+// the shipped library is always built with 0 and contains none of this): 1 = no x traffic, 2 = no correction
+// MMAs, 4 = no layer-output stores, 8 = no MUFU in the epilogue.  Results of such builds are wrong by design.
+#ifndef CF_EXP
+#define CF_EXP 0
+#endif
+constexpr int kExp = CF_EXP;
 
 struct ConvParams {                    // byte offsets inside the parameter block
     static constexpr int kFloats = 10 * 32;              // a_sc b_sc a1 b1 | b2 b3 b4 b5 b6 b7
@@ -121,12 +128,8 @@ struct TcEngine {
     DevBuf ws;
     int n_sms = 148;
     bool attr_done = false;
-    int fused_variant = 2;            // 2 = two tiles per CTA, state operand in TMEM (TK4G); 1 = TK4F (CF_TC_FUSED=1)
-    int conv_variant = 4;             // 4 = two chains + k3 operands in TMEM (tc_conv4_kernel); 3 = two chains (tc_conv3_kernel, two residual blocks); 2 = one round per position
-                                      // (tc_conv2_kernel, CF_TC_CONV=2); 1 = three rounds (tc_conv_kernel, CF_TC_CONV=1)
     bool trace_done = false;
-    int x_depth = 0;                  // x blocks prefetched into L2 ahead of the ring (CF_TC_XDEPTH); measured: no gain, extra DRAM reads
-    int dbg = 0;                      // CF_TC_DBG: timing experiments only (results become wrong)
+    const char* trace_path = nullptr; // CF_TC_TRACE=<file>: in-kernel timeline of one TK4G launch (debug; results unaffected)
     bool use_fused = true;            // CF_TC_UNFUSED=1 selects the xp + recurrence pair (TK3 + TK4)
     int fmt = kFmtBf16x3;             // operand format of the 128-wide fused GRU layers (kFmtF16E5 unless CF_TC_FMT=0 or a
                                       // cross-check variant / a network the default kernels do not cover is selected); the
@@ -157,15 +160,12 @@ TcEngine* tc_create(const HostModel& hm) {
     cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, dev);
     e->simt = simt_create(hm);
     if (const char* env = getenv("CF_TC_UNFUSED")) e->use_fused = !(env[0] == '1');
-    if (const char* env = getenv("CF_TC_DBG")) e->dbg = atoi(env);
-    if (const char* env = getenv("CF_TC_CONV")) e->conv_variant = std::min(4, std::max(1, atoi(env)));
-    if (const char* env = getenv("CF_TC_XDEPTH")) e->x_depth = std::max(0, atoi(env));
-    if (const char* env = getenv("CF_TC_FUSED")) e->fused_variant = atoi(env) == 1 ? 1 : 2;
+    e->trace_path = getenv("CF_TC_TRACE");
     {
         // fp16 + e5m2 operands need every tensor-core kernel of the pass to speak the format: the default
         // conv stack (two residual blocks) followed by fused GRU layers only
         const bool covered = hm.desc.network_type == CF_NET_RESNET_RNN && hm.n_res() == 2 && hm.conv_channels() == kC &&
-                             e->conv_variant == 4 && e->fused_variant == 2 && e->use_fused;
+                             e->use_fused;
         const char* env = getenv("CF_TC_FMT");
         e->fmt = covered && !(env && env[0] == '0') ? kFmtF16E5 : kFmtBf16x3;
     }
@@ -335,215 +335,8 @@ __global__ void tc_pack_a_kernel(const float* __restrict__ in, int K, int64_t n_
 constexpr uint32_t kSliceBytes = 2u * 128 * kC * 2;       // one position of a tile as A operand: 16 KB
 constexpr uint32_t kConvSmem = ConvParams::kBytes + 10 * kSliceBytes + 35 * 128 * 4 + 256;   // tc_conv2: O1 ring of 4
 
-__device__ __forceinline__ void store_a_row32(uint8_t* slice, int row, const float* v) {
-    // 32 channels of one window into an operand slice {hi, lo} x [4][128][8]
-#pragma unroll
-    for (int kg = 0; kg < 4; ++kg) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split_bf16x2(v[kg * 8 + 2 * i], v[kg * 8 + 2 * i + 1], hi[i], lo[i]);
-        *reinterpret_cast<uint4*>(slice + kg * 2048 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(slice + 8192 + kg * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-
-// 3-pass split-bf16 MMA of one K = 32 operand slice against one [32 x N] weight matrix.
-template <int N>
-__device__ __forceinline__ void conv_mma(uint32_t tmem_d, uint32_t a_slice, uint32_t w_mat, bool first) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, N);
-#pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t ap = a_slice + (pass == 1 ? 8192u : 0u);
-        const uint32_t wp = w_mat + (pass == 2 ? (uint32_t)(kC * N * 2) : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-            umma_bf16(tmem_d, make_smem_desc(ap + kk * 4096, 2048, 128), make_smem_desc(wp + kk * 2 * (N * 16), N * 16, 128),
-                      idesc, !(first && pass == 0 && kk == 0));
-    }
-}
-
-template <int NRES>
-__global__ void __launch_bounds__(128, 1)
-tc_conv_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
-               const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
-               const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* prm = smem;
-    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 3 slices
-    uint8_t* o2 = o1 + 3 * kSliceBytes;
-    uint8_t* y0 = o2 + kSliceBytes;
-    uint8_t* p1 = y0 + kSliceBytes;                   // ring of 3 slices
-    uint8_t* p2 = p1 + 3 * kSliceBytes;
-    float* xs = reinterpret_cast<float*>(p2 + kSliceBytes);      // [35][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 35 * 128); // 3 round barriers + parameter barrier
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    const float* fp = reinterpret_cast<const float*>(prm);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = threadIdx.x;                      // window of the tile = TMEM lane
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-        fence_mbar_init();
-        mbar_expect_tx(&bars[3], ConvParams::kBytes);
-        bulk_g2s(prm, params, ConvParams::kBytes, &bars[3]);
-    }
-    if (warp == 0) tmem_alloc<256>(tmem_slot);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    mbar_wait(&bars[3], 0);
-    const uint32_t prm_u = smem_u32(prm);
-    const uint32_t o1_u = smem_u32(o1), o2_u = smem_u32(o2), y0_u = smem_u32(y0), p1_u = smem_u32(p1), p2_u = smem_u32(p2);
-    // TMEM columns: o2 0, o3 32, [sc1|p1] slots 64 / 128, p2 192, p3 224
-    uint32_t round = 0;                               // completed uses of each round barrier
-
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- gather + normalise this thread's window (infer.py:101-105, 32-38; f64 -> f32 feed)
-        const int64_t g = (tile0 + tile) * kTileWindows + row;
-        const int nv = valid[g];
-        {
-            const int64_t s0 = src[g];
-            double shift = 0.0, scale = 1.0;
-            if (raw && nv > 0) { const int r = read[g]; shift = stats[2 * r]; scale = stats[2 * r + 1]; }
-            for (int t = 0; t < kWindow; ++t) {
-                float v = 0.f;
-                if (t < nv) v = raw ? (float)(((double)raw[s0 + t] - shift) / scale) : xwin[s0 + t];
-                xs[t * 128 + row] = v;
-            }
-        }
-        const int last_u = NRES == 2 ? kWindow + 2 : kWindow;
-        for (int u = 0; u <= last_u; ++u, ++round) {
-            const int tb = u - 1, tc = u - 3;
-            const bool has_b = tb >= 0 && tb < kWindow;
-            const bool has_c = NRES == 2 && tc >= 0 && tc < kWindow;
-            // ---- phase 1: o1[u] = relu(x a1 + b1)
-            if (u < kWindow) {
-                const float x = xs[u * 128 + row];
-                float v[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(fmaf(x, fp[64 + c], fp[96 + c]), 0.f);
-                store_a_row32(o1 + (u % 3) * kSliceBytes, row, v);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            // ---- round 1: o2[tb], p2[tc]
-            if (threadIdx.x == 0) {
-                tc_fence_after_sync();
-                if (has_b) {
-                    bool first = true;
-                    for (int tap = 0; tap < 3; ++tap) {
-                        const int tt = tb + tap - 1;
-                        if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma<32>(tmem + 0, o1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first);
-                        first = false;
-                    }
-                }
-                if (has_c) {
-                    bool first = true;
-                    for (int tap = 0; tap < 3; ++tap) {
-                        const int tt = tc + tap - 1;
-                        if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma<32>(tmem + 192, p1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW6 + tap * 4096, first);
-                        first = false;
-                    }
-                }
-                umma_commit(&bars[0]);
-            }
-            mbar_wait(&bars[0], round & 1);
-            tc_fence_after_sync();
-            if (has_b) {
-                float v[32];
-                tmem_ld16(t_lane + 0, v);
-                tmem_ld16(t_lane + 16, v + 16);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + fp[128 + c], 0.f);          // b2
-                store_a_row32(o2, row, v);
-            }
-            if (has_c) {
-                float v[32];
-                tmem_ld16(t_lane + 192, v);
-                tmem_ld16(t_lane + 208, v + 16);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + fp[256 + c], 0.f);          // b6
-                store_a_row32(p2, row, v);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            // ---- round 2: o3[tb], p3[tc]
-            if (threadIdx.x == 0) {
-                tc_fence_after_sync();
-                if (has_b) conv_mma<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true);
-                if (has_c) conv_mma<32>(tmem + 224, p2_u, prm_u + ConvParams::kW7, true);
-                umma_commit(&bars[1]);
-            }
-            mbar_wait(&bars[1], round & 1);
-            tc_fence_after_sync();
-            if (has_b) {
-                float v[32];
-                tmem_ld16(t_lane + 32, v);
-                tmem_ld16(t_lane + 48, v + 16);
-                const float x = xs[tb * 128 + row];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float sc = fmaf(x, fp[c], fp[32 + c]);                           // shortcut BN(conv k1)
-                    v[c] = fmaxf(fmaxf(v[c] + fp[160 + c], 0.f) + sc, 0.f);                 // b3
-                }
-                if (NRES == 2) {
-                    store_a_row32(y0, row, v);
-                } else {
-                    uint8_t* dst = reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + tb) * kSliceBytes;
-                    store_a_row32(dst, row, v);
-                }
-            }
-            if (has_c) {
-                float v[32], sc[32];
-                tmem_ld16(t_lane + 224, v);
-                tmem_ld16(t_lane + 240, v + 16);
-                const uint32_t slot = t_lane + 64 + (tc & 1) * 64;
-                tmem_ld16(slot, sc);
-                tmem_ld16(slot + 16, sc + 16);
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    v[c] = fmaxf(fmaxf(v[c] + fp[288 + c], 0.f) + (sc[c] + fp[192 + c]), 0.f);   // b7, b4
-                uint8_t* dst = reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + tc) * kSliceBytes;
-                store_a_row32(dst, row, v);
-            }
-            if (NRES == 2) {
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                __syncthreads();
-                // ---- round 3: [sc1 | p1][tb] = y0 [W4 | W5]
-                if (threadIdx.x == 0) {
-                    tc_fence_after_sync();
-                    if (has_b) conv_mma<64>(tmem + 64 + (tb & 1) * 64, y0_u, prm_u + ConvParams::kW45, true);
-                    umma_commit(&bars[2]);
-                }
-                mbar_wait(&bars[2], round & 1);
-                tc_fence_after_sync();
-                if (has_b) {
-                    float v[32];
-                    const uint32_t slot = t_lane + 64 + (tb & 1) * 64 + 32;
-                    tmem_ld16(slot, v);
-                    tmem_ld16(slot + 16, v + 16);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + fp[224 + c], 0.f);      // b5
-                    store_a_row32(p1 + (tb % 3) * kSliceBytes, row, v);
-                }
-            }
-        }
-        __syncthreads();          // xs is rewritten by the next tile
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
-}
-
 // ====================================================================== TK2 v2: deeper skew, one round per position
-// Same mathematics and operand layouts as tc_conv_kernel; the five MMA stages of the two residual
+// The residual stack with every operand slice in shared memory; the five MMA stages of the two residual
 // blocks are skewed over time so that ALL of them are issued in one batch per iteration u:
 //   o2[u-1], o3[u-2], [sc1|p1][u-3], p2[u-5], p3[u-6]
 // followed by ONE epilogue pass that consumes the five accumulators (all TMEM loads in flight at
@@ -754,262 +547,6 @@ tc_conv2_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
     if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
-// ====================================================================== TK2 v3: the two residual blocks as two chains
-// Same mathematics, operand layouts and accumulator skew as tc_conv2_kernel (NRES == 2 only), but
-// the work of a position is split by residual block into two independently clocked chains so that
-// the MMA batch of one block runs on the tensor pipe while the other block's epilogue runs:
-//   chain X (block 0): batch o2[u-1], o3[u-2]                 -> epilogue writes o2, y0, o1[u+2]
-//   chain Y (block 1): batch [sc1|p1][u-3], p2[u-5], p3[u-6]  -> epilogue writes p1, p2, y1 (global)
-//   warps 0-7 / 8-15 : epilogue of X / Y, thread = (window, 16 of the 32 channels)
-//   warp 16 / 17     : MMA issuer of X / Y (warp-converged, elected lane)
-// The only coupling is y0 (output of block 0 = input of block 1).  It lives in TENSOR MEMORY as the
-// A operand of the [sc1|p1] MMAs (".ts" form: no shared-memory slice, no A-operand smem reads),
-// in a ring of 4 slots with full (X epilogue -> Y issuer) / empty (tcgen05.commit -> X epilogue)
-// barriers, so X may run up to three positions ahead of Y.
-// TMEM: o2 0, o3 32, p2 64, p3 96, [sc1|p1] ring of 4 at 128 + 64 k, y0 ring of 4 at 384 + 32 k
-// (per slot: hi K 0-15 | hi K 16-31 | lo K 0-15 | lo K 16-31, 8 columns each).
-constexpr uint32_t kConv3Smem = ConvParams::kBytes + 9 * kSliceBytes + 35 * 128 * 4 + 256;
-
-__global__ void __launch_bounds__(576, 1)
-tc_conv3_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
-                const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
-                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* prm = smem;
-    uint8_t* o1 = smem + ConvParams::kBytes;          // ring of 4 slices (o1 is produced two positions ahead)
-    uint8_t* o2 = o1 + 4 * kSliceBytes;
-    uint8_t* p1 = o2 + kSliceBytes;                   // ring of 3 slices
-    uint8_t* p2 = p1 + 3 * kSliceBytes;
-    float* xs = reinterpret_cast<float*>(p2 + kSliceBytes);      // [35][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 35 * 128);
-    uint64_t* bar_ready_x = &bars[0];
-    uint64_t* bar_mma_x = &bars[1];
-    uint64_t* bar_ready_y = &bars[2];
-    uint64_t* bar_mma_y = &bars[3];
-    uint64_t* bar_prm = &bars[4];
-    uint64_t* bar_y0_full = &bars[5];                 // [4]
-    uint64_t* bar_y0_empty = &bars[9];                // [4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    const float* fp = reinterpret_cast<const float*>(prm);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        mbar_init(bar_ready_x, 8);
-        mbar_init(bar_mma_x, 1);
-        mbar_init(bar_ready_y, 8);
-        mbar_init(bar_mma_y, 1);
-        mbar_init(bar_prm, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&bar_y0_full[i], 8); mbar_init(&bar_y0_empty[i], 1); }
-        fence_mbar_init();
-        mbar_expect_tx(bar_prm, ConvParams::kBytes);
-        bulk_g2s(prm, params, ConvParams::kBytes, bar_prm);
-    }
-    if (warp == 16) tmem_alloc<512>(tmem_slot);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    constexpr int kLastX = kWindow + 1;               // o3[34] at u = 36
-    constexpr int kFirstY = 3, kLastY = kWindow + 5;  // [sc1|p1][0] at u = 3, p3[34] at u = 40
-    constexpr uint32_t kTmY0 = 384;
-    mbar_wait(bar_prm, 0);
-
-    if (warp == 16) {
-        // ------------------------------------------------------------ issuer of chain X
-        const uint32_t elected = elect_one();
-        const uint32_t prm_u = smem_u32(prm), o1_u = smem_u32(o1), o2_u = smem_u32(o2);
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int u = 0; u <= kLastX; ++u, ++it) {
-                mbar_wait(bar_ready_x, it & 1);
-                tc_fence_after_sync();
-                const int t1 = u - 1, t2 = u - 2;
-                if (t1 >= 0 && t1 < kWindow) {
-                    bool first = true;
-#pragma unroll
-                    for (int tap = 0; tap < 3; ++tap) {
-                        const int tt = t1 + tap - 1;
-                        if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_pred<32>(tmem + 0, o1_u + (tt & 3) * kSliceBytes, prm_u + ConvParams::kW2 + tap * 4096, first, elected);
-                        first = false;
-                    }
-                }
-                if (t2 >= 0 && t2 < kWindow) conv_mma_pred<32>(tmem + 32, o2_u, prm_u + ConvParams::kW3, true, elected);
-                umma_commit_pred(bar_mma_x, elected);
-            }
-        }
-    } else if (warp == 17) {
-        // ------------------------------------------------------------ issuer of chain Y
-        const uint32_t elected = elect_one();
-        const uint32_t prm_u = smem_u32(prm), p1_u = smem_u32(p1), p2_u = smem_u32(p2);
-        constexpr uint32_t idesc64 = make_idesc_bf16(128, 64);
-        uint32_t it = 0, ny = 0;                       // ny: y0 positions consumed so far
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int u = kFirstY; u <= kLastY; ++u, ++it) {
-                mbar_wait(bar_ready_y, it & 1);
-                tc_fence_after_sync();
-                const int t3 = u - 3, t4 = u - 5, t5 = u - 6;
-                if (t3 < kWindow) {
-                    const uint32_t slot = ny & 3;
-                    mbar_wait(&bar_y0_full[slot], (ny >> 2) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t a = tmem + kTmY0 + slot * 32, d = tmem + 128 + (t3 & 3) * 64;
-                    const uint32_t w = prm_u + ConvParams::kW45;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t ap = a + (pass == 1 ? 16u : 0u);
-                        const uint32_t wp = w + (pass == 2 ? (uint32_t)(kC * 64 * 2) : 0u);
-#pragma unroll
-                        for (int kk = 0; kk < 2; ++kk)
-                            umma_bf16_ts_pred(d, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc64,
-                                              !(pass == 0 && kk == 0), elected);
-                    }
-                    umma_commit_pred(&bar_y0_empty[slot], elected);
-                    ++ny;
-                }
-                if (t4 >= 0 && t4 < kWindow) {
-                    bool first = true;
-#pragma unroll
-                    for (int tap = 0; tap < 3; ++tap) {
-                        const int tt = t4 + tap - 1;
-                        if (tt < 0 || tt >= kWindow) continue;
-                        conv_mma_pred<32>(tmem + 64, p1_u + (tt % 3) * kSliceBytes, prm_u + ConvParams::kW6 + tap * 4096, first, elected);
-                        first = false;
-                    }
-                }
-                if (t5 >= 0 && t5 < kWindow) conv_mma_pred<32>(tmem + 96, p2_u, prm_u + ConvParams::kW7, true, elected);
-                umma_commit_pred(bar_mma_y, elected);
-            }
-        }
-    } else {
-        const int ew = warp & 7;                      // warp within its epilogue group
-        const int q = ew & 3, ch = ew >> 2;
-        const int row = q * 32 + lane;
-        const int c0 = ch * 16;
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + c0;
-        auto relu_bias = [&](uint32_t* r, int slot, float* v) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(fp + 32 * slot + c0 + i);
-                v[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
-                v[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
-                v[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
-                v[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
-            }
-        };
-        if (warp < 8) {
-            // -------------------------------------------------------- epilogue of chain X
-            auto make_o1 = [&](int t) {               // o1[t] = relu(x a1 + b1) on CUDA cores
-                const float x = xs[t * 128 + row];
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(x, fp[64 + c0 + i], fp[96 + c0 + i]), 0.f);
-                store_a_row16(o1 + (t & 3) * kSliceBytes, row, c0, v);
-            };
-            const uint32_t t_y0 = tmem + ((uint32_t)(q * 32) << 16) + kTmY0 + ch * 8;
-            uint32_t it = 0, ny = 0;                  // ny: y0 positions produced so far
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                // gather + normalise (infer.py:101-105, 32-38): the two threads of a window split its 35 samples
-                asm volatile("bar.sync 1, 256;" ::: "memory");        // previous tile's readers of xs are done
-                {
-                    const int64_t g = (tile0 + tile) * kTileWindows + row;
-                    const int nv = valid[g];
-                    const int64_t s0 = src[g];
-                    double shift = 0.0, scale = 1.0;
-                    if (raw && nv > 0) { const int r = read[g]; shift = stats[2 * r]; scale = stats[2 * r + 1]; }
-                    const int tb = ch ? 18 : 0, te = ch ? kWindow : 18;
-                    for (int t = tb; t < te; ++t) {
-                        float v = 0.f;
-                        if (t < nv) v = raw ? (float)(((double)raw[s0 + t] - shift) / scale) : xwin[s0 + t];
-                        xs[t * 128 + row] = v;
-                    }
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                make_o1(0);
-                make_o1(1);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_ready_x);
-                for (int u = 0; u <= kLastX; ++u, ++it) {
-                    const int t1 = u - 1, t2 = u - 2;
-                    const bool h1 = t1 >= 0 && t1 < kWindow, h2 = t2 >= 0 && t2 < kWindow;
-                    mbar_wait(bar_mma_x, it & 1);
-                    tc_fence_after_sync();
-                    uint32_t r1[16], r2[16];
-                    if (h1) tmem_ld16_nowait(t_lane + 0, r1);
-                    if (h2) tmem_ld16_nowait(t_lane + 32, r2);
-                    tmem_ld_wait();
-                    tc_fence_before_sync();
-                    float v[16];
-                    if (h1) { relu_bias(r1, 4, v); store_a_row16(o2, row, c0, v); }              // b2
-                    // o2 (and o1[u+1], made one iteration ago) are all the next X batch reads
-                    if (u < kLastX) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_ready_x);
-                    }
-                    if (h2) {
-                        relu_bias(r2, 5, v);                                                     // b3
-                        const float x = xs[t2 * 128 + row];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + fmaf(x, fp[c0 + i], fp[32 + c0 + i]), 0.f);   // + shortcut
-                        uint32_t hi[8], lo[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-                        const uint32_t slot = ny & 3;
-                        if (ny >= 4) mbar_wait(&bar_y0_empty[slot], ((ny >> 2) - 1) & 1);
-                        tc_fence_after_sync();
-                        tmem_st8_u32(t_y0 + slot * 32, hi);
-                        tmem_st8_u32(t_y0 + slot * 32 + 16, lo);
-                        tmem_st_wait();
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_y0_full[slot]);
-                        ++ny;
-                    }
-                    if (u + 2 < kWindow) make_o1(u + 2);
-                }
-            }
-        } else {
-            // -------------------------------------------------------- epilogue of chain Y
-            uint32_t it = 0;
-            if (lane == 0) mbar_arrive(bar_ready_y);          // nothing to prepare for the first batch
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int u = kFirstY; u <= kLastY; ++u, ++it) {
-                    const int t3 = u - 3, t4 = u - 5, t5 = u - 6;
-                    const bool h3 = t3 < kWindow, h4 = t4 >= 0 && t4 < kWindow, h5 = t5 >= 0 && t5 < kWindow;
-                    mbar_wait(bar_mma_y, it & 1);
-                    tc_fence_after_sync();
-                    uint32_t r3[16], r4[16], r5[16], rs[16];
-                    if (h3) tmem_ld16_nowait(t_lane + 128 + (t3 & 3) * 64 + 32, r3);
-                    if (h4) tmem_ld16_nowait(t_lane + 64, r4);
-                    if (h5) {
-                        tmem_ld16_nowait(t_lane + 96, r5);
-                        tmem_ld16_nowait(t_lane + 128 + (t5 & 3) * 64, rs);
-                    }
-                    tmem_ld_wait();
-                    tc_fence_before_sync();
-                    float v[16];
-                    if (h3) { relu_bias(r3, 7, v); store_a_row16(p1 + (t3 % 3) * kSliceBytes, row, c0, v); }   // b5
-                    if (h4) { relu_bias(r4, 8, v); store_a_row16(p2, row, c0, v); }              // b6
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_ready_y);
-                    if (h5) {
-                        relu_bias(r5, 9, v);                                                     // b7
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + (__uint_as_float(rs[i]) + fp[192 + c0 + i]), 0.f);   // + sc1 + b4
-                        store_a_row16(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 16) tmem_dealloc<512>(tmem);
-}
-
 // ====================================================================== operand formats
 // FMT 0 = split bf16, three MMAs per K = 16 chunk (bf16x3).  FMT 1 = fp16 + e5m2 corrections, two
 // MMAs per chunk ("f16e5", tc_ptx.cuh).  Both use the same byte positions everywhere: plane 0 holds
@@ -1072,7 +609,7 @@ __device__ __forceinline__ void conv_mma_f(uint32_t tmem_d, uint32_t a_slice, ui
 }
 
 // ====================================================================== TK2 v4: two chains, k = 3 operands in tensor memory
-// tc_conv3_kernel with the A operands of both k = 3 convolutions (the o1 and p1 rings) and y0 held in
+// The two residual blocks as two independently clocked chains, with the A operands of both k = 3 convolutions (the o1 and p1 rings) and y0 held in
 // TENSOR MEMORY: an N = 32 MMA that reads its 4 KB A operand from shared memory is bound by that
 // read (~38 cycles for 17 cycles of math); the ".ts" form only fetches the 1 KB weight slice.
 // To make room the [sc1|p1] accumulator is single-buffered: the epilogue thread that reads p1 also
@@ -1744,297 +1281,6 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
     if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
-// ====================================================================== TK4F: fused GRU layer
-// Input projection + recurrence of one GRU layer in one kernel: the concat([x, h]) matmuls of
-// tf.contrib.rnn.GRUCell (rnn_class.py:146) exactly as TensorFlow does them, so the hoisted
-// projection xp never goes to HBM (it was 1536 B/sample/layer written and read back).
-//
-// CTA = one direction, one tile of 128 windows at a time (persistent over tiles).  Resident in
-// shared memory: the direction's weights [x rows; h rows] x [r|u|c] as split-bf16 B operands
-// (147 KB for a 128-wide input), the state operand h / r*h (32 KB) and a 4-stage ring through
-// which the layer input x_t streams in K = 16 chunks by bulk TMA copies.  Two TMEM accumulator
-// sets (gates 128 + candidate 64 columns each): while the epilogue works on step s, the tensor
-// core already accumulates the x part of step s+1 into the other set - only the K = 64 state
-// part of each matmul sits on the recurrent critical path.
-//   warps 0-15: epilogue; thread = (window, quarter of the hidden units), h and u in registers
-//   warp 16   : MMA issuer (+ TMEM owner); candidate-state MMAs take priority over x chunks
-//   warp 17   : producer (weights once, then the x ring)
-template <int KX> struct GruFusedCfg {
-    static constexpr int kChunks = KX / 16;                              // x K-chunks per step
-    static constexpr int kStages = KX >= 128 ? 5 : 8;
-    static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
-    static constexpr uint32_t kWgh = kWx + 2u * KX * kNX * 2;            // {hi, lo} x [8][128][8]
-    static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;           // {hi, lo} x [8][64][8]
-    static constexpr uint32_t kWBytes = kWch + 2u * kH * 64 * 2;         // (KX + 64) * 192 * 4
-    static constexpr uint32_t kHBuf = kWBytes;                           // {hi, lo} x [8][128][8]
-    static constexpr uint32_t kRing = kHBuf + kGruABytes;                // kStages x {hi, lo} x [2][128][8]
-    static constexpr uint32_t kBias = kRing + kStages * 8192;            // 192 floats
-    static constexpr uint32_t kBars = kBias + 192 * 4;
-    static constexpr uint32_t kSmem = kBars + 256;
-};
-
-template <int KX>
-__global__ void __launch_bounds__(576, 1)
-tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
-                    const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
-                    const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int dbg) {
-    using Cfg = GruFusedCfg<KX>;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
-    uint64_t* bar_g = &bars[0];
-    uint64_t* bar_c = &bars[1];
-    uint64_t* bar_rh = &bars[2];
-    uint64_t* bar_h = &bars[3];
-    uint64_t* full = &bars[4];                    // [kStages]
-    uint64_t* empty = &bars[4 + Cfg::kStages];    // [kStages]
-    uint64_t* w_bar = &bars[4 + 2 * Cfg::kStages];
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[5 + 2 * Cfg::kStages]);
-    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int dir = blockIdx.x & 1;
-    const int slot = blockIdx.x >> 1, n_slots = gridDim.x >> 1;
-    const int my_tiles = slot < n_tiles ? (n_tiles - slot + n_slots - 1) / n_slots : 0;
-    const int total_steps = my_tiles * kWindow;
-
-    if (threadIdx.x == 0) {
-        mbar_init(bar_g, 1);
-        mbar_init(bar_c, 1);
-        mbar_init(bar_rh, 512);
-        mbar_init(bar_h, 512);
-        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(w_bar, 1);
-        fence_mbar_init();
-    }
-    if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x];
-    if (warp == 16) tmem_alloc<512>(tmem_slot);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    // block (tile, t) visited at flattened step gs of this CTA
-    auto blk_of = [&](int gs) -> size_t {
-        const int ti = gs / kWindow, s = gs - ti * kWindow;
-        return (size_t)(slot + ti * n_slots) * kWindow + (dir ? kWindow - 1 - s : s);
-    };
-
-    if (warp == 17) {
-        // ------------------------------------------------------------ producer
-        if (lane == 0) {
-            mbar_expect_tx(w_bar, Cfg::kWBytes);
-            const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
-            for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
-                const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
-                bulk_g2s(smem + off, wsrc + off, n, w_bar);
-            }
-            constexpr size_t plane = (size_t)128 * KX * 2;          // bytes of one plane of an x block
-            uint32_t c = 0;
-            constexpr int kAhead = 3;                 // blocks pulled into L2 ahead of the ring (hides HBM latency)
-            for (int gs = 0; gs < kAhead && gs < total_steps; ++gs)
-                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs) * 2 * plane, 2 * plane);
-            for (int gs = 0; gs < total_steps; ++gs) {
-                const uint8_t* xb = reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs) * 2 * plane;
-                if (gs + kAhead < total_steps)
-                    bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(x_blocks) + blk_of(gs + kAhead) * 2 * plane, 2 * plane);
-                for (int kk = 0; kk < Cfg::kChunks; ++kk, ++c) {
-                    const int st = c % Cfg::kStages;
-                    mbar_wait(&empty[st], ((c / Cfg::kStages) & 1) ^ 1);
-                    if (dbg & 1) { mbar_arrive(&full[st]); continue; }      // timing experiment: no x traffic
-                    mbar_expect_tx(&full[st], 8192);
-                    uint8_t* dst = smem + Cfg::kRing + st * 8192;
-                    bulk_g2s(dst, xb + kk * 4096, 4096, &full[st]);
-                    bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, &full[st]);
-                }
-            }
-        }
-    } else if (warp == 16) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_g = make_idesc_bf16(128, 2 * kH);
-            constexpr uint32_t idesc_c = make_idesc_bf16(128, kH);
-            constexpr uint32_t idesc_x = make_idesc_bf16(128, kNX);
-            const uint32_t s0 = smem_u32(smem);
-            const uint32_t hbuf = s0 + Cfg::kHBuf, ring = s0 + Cfg::kRing;
-            uint32_t c = 0;                          // x chunks consumed so far
-            // x part of one chunk of step `gs_next` into accumulator set `buf`
-            auto issue_x_chunk = [&](int kk, uint32_t buf) {
-                const int st = c % Cfg::kStages;
-                const uint32_t a0 = ring + st * 8192;
-                const uint32_t dg = tmem + buf * 256;
-#pragma unroll
-                for (int pass = 0; pass < ((dbg & 2) ? 1 : 3); ++pass) {   // dbg & 2: timing experiment, single pass
-                    const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
-                    const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
-                    umma_bf16(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0);   // gates | candidate
-                }
-                umma_commit(&empty[st]);
-                ++c;
-            };
-            mbar_wait(w_bar, 0);
-            if (total_steps > 0) {
-                for (int kk = 0; kk < Cfg::kChunks; ++kk) {            // prologue: x part of step 0
-                    mbar_wait(&full[c % Cfg::kStages], (c / Cfg::kStages) & 1);
-                    tc_fence_after_sync();
-                    issue_x_chunk(kk, 0);
-                }
-            }
-            for (int gs = 0; gs < total_steps; ++gs) {
-                const uint32_t buf = gs & 1, par = gs & 1;
-                const uint32_t dg = tmem + buf * 256, dc = dg + 2 * kH;
-                mbar_wait(bar_h, par);
-                tc_fence_after_sync();
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {                 // state part of the gates
-                    const uint32_t ap = hbuf + (pass == 1 ? 128u * kH * 2 : 0u);
-                    const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
-#pragma unroll
-                    for (int kk = 0; kk < kH / 16; ++kk)
-                        umma_bf16(dg, make_smem_desc(ap + kk * 4096, 2048, 128),
-                                  make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1);
-                }
-                umma_commit(bar_g);
-                int xk = 0;
-                const int nx = gs + 1 < total_steps ? Cfg::kChunks : 0;
-                bool c_done = false;
-                while (xk < nx || !c_done) {
-                    if (!c_done && mbar_test_wait(bar_rh, par)) {
-                        tc_fence_after_sync();
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {         // state part of the candidate
-                            const uint32_t ap = hbuf + (pass == 1 ? 128u * kH * 2 : 0u);
-                            const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
-#pragma unroll
-                            for (int kk = 0; kk < kH / 16; ++kk)
-                                umma_bf16(dc, make_smem_desc(ap + kk * 4096, 2048, 128),
-                                          make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1);
-                        }
-                        umma_commit(bar_c);
-                        c_done = true;
-                    } else if (xk < nx && mbar_test_wait(&full[c % Cfg::kStages], (c / Cfg::kStages) & 1)) {
-                        tc_fence_after_sync();
-                        issue_x_chunk(xk, buf ^ 1);
-                        ++xk;
-                    }
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------ epilogue
-        // 16 warps: TMEM lane quadrant q = warp % 4 (hardware rule), quarter qt of the hidden units.
-        const int q = warp & 3, qt = warp >> 2;
-        const int row = q * 32 + lane;
-        const int j0 = qt * 16;
-        uint8_t* a_hi = smem + Cfg::kHBuf + row * 16 + (j0 / 8) * 2048;      // two k-groups: +0, +2048
-        uint8_t* a_lo = a_hi + 128 * kH * 2;
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + j0;
-        const float4* b_r = reinterpret_cast<const float4*>(bias_s + j0);
-        const float4* b_u = reinterpret_cast<const float4*>(bias_s + kH + j0);
-        const float4* b_c = reinterpret_cast<const float4*>(bias_s + 2 * kH + j0);
-        const float* hw = head_w ? head_w + dir * kH + j0 : nullptr;
-        float h[16], u[16];
-        int gs = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = 0.f;
-            *reinterpret_cast<uint4*>(a_hi) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a_hi + 2048) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a_lo) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a_lo + 2048) = make_uint4(0, 0, 0, 0);
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            mbar_arrive(bar_h);
-            for (int s = 0; s < kWindow; ++s, ++gs) {
-                const uint32_t par = gs & 1;
-                const uint32_t tb = t_lane + (gs & 1) * 256;
-                const size_t blk = blk_of(gs);
-                // ---- gates: both TMEM loads in flight, reset gate first (the candidate MMA waits for r*h)
-                mbar_wait(bar_g, par);
-                tc_fence_after_sync();
-                uint32_t ar[16], au[16];
-                tmem_ld16_nowait(tb, ar);
-                tmem_ld16_nowait(tb + kH, au);
-                tmem_ld_wait();
-                {
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float z[4], r[4];
-                        const float4 b4 = b_r[i >> 2];
-                        z[0] = __uint_as_float(ar[i]) + b4.x; z[1] = __uint_as_float(ar[i + 1]) + b4.y;
-                        z[2] = __uint_as_float(ar[i + 2]) + b4.z; z[3] = __uint_as_float(ar[i + 3]) + b4.w;
-                        sigmoid4_z(z, r);
-                        split_bf16x2(r[0] * h[i], r[1] * h[i + 1], hi[i >> 1], lo[i >> 1]);
-                        split_bf16x2(r[2] * h[i + 2], r[3] * h[i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
-                    }
-                    *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(a_hi + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(a_lo + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                }
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                mbar_arrive(bar_rh);
-                // ---- update gate while the candidate MMA runs
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    float z[4];
-                    const float4 b4 = b_u[i >> 2];
-                    z[0] = __uint_as_float(au[i]) + b4.x; z[1] = __uint_as_float(au[i + 1]) + b4.y;
-                    z[2] = __uint_as_float(au[i + 2]) + b4.z; z[3] = __uint_as_float(au[i + 3]) + b4.w;
-                    sigmoid4_z(z, u + i);
-                }
-                // ---- candidate, new state h = c + u (h - c)
-                mbar_wait(bar_c, par);
-                tc_fence_after_sync();
-                uint32_t ac[16];
-                tmem_ld16_nowait(tb + 2 * kH, ac);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                {
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        float z[4], cv[4];
-                        const float4 b4 = b_c[i >> 2];
-                        z[0] = __uint_as_float(ac[i]) + b4.x; z[1] = __uint_as_float(ac[i + 1]) + b4.y;
-                        z[2] = __uint_as_float(ac[i + 2]) + b4.z; z[3] = __uint_as_float(ac[i + 3]) + b4.w;
-                        tanh4_z(z, cv);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
-                        split_bf16x2(h[i], h[i + 1], hi[i >> 1], lo[i >> 1]);
-                        split_bf16x2(h[i + 2], h[i + 3], hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
-                    }
-                    *reinterpret_cast<uint4*>(a_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(a_hi + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(a_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(a_lo + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                    if (s + 1 < kWindow) {               // hand h to the next step before the global stores
-                        fence_proxy_async_smem();
-                        mbar_arrive(bar_h);
-                    }
-                    if (y_out) {
-                        // next layer's A operand: block {hi, lo} x [16][128][8], features dir*64 + j
-                        __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 8;
-                        *reinterpret_cast<uint4*>(yb) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(yb + 128 * 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                        *reinterpret_cast<uint4*>(yb + 128 * 2 * kH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + 128 * 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                    }
-                }
-                if (head_part) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc = fmaf(h[i], __ldg(hw + i), acc);
-                    head_part[((blk * 2 + dir) * 4 + qt) * 128 + row] = acc;
-                }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 16) tmem_dealloc<512>(tmem);
-}
-
 // ====================================================================== TK4G: fused GRU layer, two tiles per CTA
 // Same mathematics as TK4F, restructured so that the tensor pipe never idles behind one chain's
 // serial MMA -> epilogue -> MMA dependency: a CTA runs TWO independent chains (two tiles of the
@@ -2042,30 +1288,35 @@ tc_gru_fused_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ b
 // operand h / r*h no longer lives in shared memory: the epilogue writes it (packed, in the operand
 // format FMT) into tensor memory with tcgen05.st and the state-part MMAs read A from TMEM (".ts" form).
 // TMEM per chain (256 columns): gates accumulator 0..127, candidate 128..191, A plane 0 192..223,
-// A plane 1 224..255.  Shared memory: weights (147 KB) + one 5-stage x ring per chain (80 KB).
+// A plane 1 224..255.  Shared memory: weights (147 KB) + ONE 10-stage x ring (80 KB) that both chains
+// consume in the fixed order (step 0, chain 0), (step 0, chain 1), (step 1, chain 0), ...: with a private
+// 5-stage ring per chain only 5 of a step's 8 chunks could be requested before the step's x part began,
+// so the last three arrived a full HBM latency later (x part 4 400-4 900 cycles for 1 536 of MMA time);
+// in the shared ring a step's chunks are all requested while the OTHER chain's x part runs.
 //   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
 //   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
-//   warp 18          : lanes 0 / 1 = producer of chain 0 / 1 (weights once, then the chain's x ring)
+//   warp 18          : lane 0 = producer (weights once, then the x ring)
 template <int KX> struct GruF2Cfg {
     static constexpr int kChunks = KX / 16;
-    static constexpr int kStages = 5;
+    static constexpr int kStages = 10;                                    // ONE ring shared by both chains (see the producer)
     static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
     static constexpr uint32_t kWgh = kWx + 2u * KX * kNX * 2;
     static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;
     static constexpr uint32_t kWBytes = kWch + 2u * kH * 64 * 2;
-    static constexpr uint32_t kRing = kWBytes;                            // [chain][stage] x 8 KB
-    static constexpr uint32_t kBias = kRing + 2u * kStages * 8192;
+    static constexpr uint32_t kRing = kWBytes;                            // [stage] x 8 KB
+    static constexpr uint32_t kBias = kRing + (uint32_t)kStages * 8192;
     static constexpr uint32_t kBars = kBias + 192 * 4;
     static constexpr uint32_t kSmem = kBars + 512;
-    // barrier indices inside a chain's group of 16 (5 + 2 * kStages <= 16)
-    static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarFull = 5, kBarEmpty = 5 + kStages;
+    // barriers: a chain's group of 8, then the ring's full / empty pairs, then the weight barrier
+    static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarXdone = 5;
+    static constexpr int kBarFull = 16, kBarEmpty = 16 + kStages, kBarW = 16 + 2 * kStages;
 };
 
 template <int KX, int FMT, int FMT_OUT>
 __global__ void __launch_bounds__(608, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
-                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles, int kXDepth,
+                     const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles,
                      long long* __restrict__ trace) {
     using Cfg = GruF2Cfg<KX>;
     // debug timeline (CF_TC_TRACE): block 0 records (tag, SM clock) pairs for steps 36..39 of each role
@@ -2081,9 +1332,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         }                                                                                          \
     } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][16], then w_bar
-    uint64_t* w_bar = &bars[32];
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[33]);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][8] per chain, ring full / empty, w_bar
+    uint64_t* w_bar = &bars[Cfg::kBarW];
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[Cfg::kBarW + 1]);
     float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2101,14 +1352,15 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 
     if (threadIdx.x == 0) {
         for (int c = 0; c < 2; ++c) {
-            uint64_t* b = &bars[16 * c];
+            uint64_t* b = &bars[8 * c];
             mbar_init(&b[Cfg::kBarG], 1);
             mbar_init(&b[Cfg::kBarC], 1);
             mbar_init(&b[Cfg::kBarRh], 8);
             mbar_init(&b[Cfg::kBarH], 8);
             mbar_init(&b[Cfg::kBarCfree], 8);
-            for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&b[Cfg::kBarFull + i], 1); mbar_init(&b[Cfg::kBarEmpty + i], 1); }
+            mbar_init(&b[Cfg::kBarXdone], 1);
         }
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&bars[Cfg::kBarFull + i], 1); mbar_init(&bars[Cfg::kBarEmpty + i], 1); }
         mbar_init(w_bar, 1);
         fence_mbar_init();
     }
@@ -2125,34 +1377,38 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 18) {
-        // ------------------------------------------------------------ producers: lane c feeds chain c
-        if (lane < 2) {
-            const int c = lane;
-            if (c == 0) {
-                mbar_expect_tx(w_bar, Cfg::kWBytes);
-                const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
-                for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
-                    const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
-                    bulk_g2s(smem + off, wsrc + off, n, w_bar);
-                }
+        // ------------------------------------------------------------ producer: weights once, then the shared x ring
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, Cfg::kWBytes);
+            const uint8_t* wsrc = wpk + (size_t)dir * Cfg::kWBytes;
+            for (uint32_t off = 0; off < Cfg::kWBytes; off += 32768) {
+                const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
+                bulk_g2s(smem + off, wsrc + off, n, w_bar);
             }
             constexpr size_t plane = (size_t)128 * KX * 2;
-            const int kAhead = kXDepth;               // blocks pulled into L2 ahead of the ring (0 = no prefetch)
             const uint8_t* xbase = reinterpret_cast<const uint8_t*>(x_blocks);
-            const int total = tiles_of(c) * kWindow;
-            uint64_t* b = &bars[16 * c];
-            for (int a = 0; a < kAhead && a < total; ++a) bulk_prefetch_l2(xbase + blk_of(c, a) * 2 * plane, 2 * plane);
-            uint32_t cn = 0;
-            for (int gs = 0; gs < total; ++gs) {
-                const uint8_t* xb = xbase + blk_of(c, gs) * 2 * plane;
-                if (gs + kAhead < total) bulk_prefetch_l2(xbase + blk_of(c, gs + kAhead) * 2 * plane, 2 * plane);
-                for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
-                    const int st = cn % Cfg::kStages;
-                    mbar_wait(&b[Cfg::kBarEmpty + st], ((cn / Cfg::kStages) & 1) ^ 1);
-                    uint8_t* dst = smem + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
-                    mbar_expect_tx(&b[Cfg::kBarFull + st], 8192);
-                    bulk_g2s(dst, xb + kk * 4096, 4096, &b[Cfg::kBarFull + st]);
-                    bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, &b[Cfg::kBarFull + st]);
+            const int total0 = tiles_of(0) * kWindow, total1 = tiles_of(1) * kWindow;     // total1 <= total0
+            uint32_t st = 0, par = 1;                     // ring position; parity of the empty barrier's previous phase
+            for (int gs = 0; gs < total0; ++gs) {
+                for (int c = 0; c < 2; ++c) {
+                    if (c == 1 && gs >= total1) break;
+                    const uint8_t* xb = xbase + blk_of(c, gs) * 2 * plane;
+                    for (int kk = 0; kk < Cfg::kChunks; ++kk) {
+                        mbar_wait(&bars[Cfg::kBarEmpty + st], par);
+                        uint8_t* dst = smem + Cfg::kRing + st * 8192;
+                        if (kExp & 1) { mbar_arrive(&bars[Cfg::kBarFull + st]); if (++st == Cfg::kStages) { st = 0; par ^= 1; } continue; }
+                        if (kExp & 16) {      // timing experiment: three quarters of the bytes
+                            mbar_expect_tx(&bars[Cfg::kBarFull + st], 6144);
+                            bulk_g2s(dst, xb + kk * 4096, 4096, &bars[Cfg::kBarFull + st]);
+                            bulk_g2s(dst + 4096, xb + plane + kk * 4096, 2048, &bars[Cfg::kBarFull + st]);
+                            if (++st == Cfg::kStages) { st = 0; par ^= 1; }
+                            continue;
+                        }
+                        mbar_expect_tx(&bars[Cfg::kBarFull + st], 8192);
+                        bulk_g2s(dst, xb + kk * 4096, 4096, &bars[Cfg::kBarFull + st]);
+                        bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, &bars[Cfg::kBarFull + st]);
+                        if (++st == Cfg::kStages) { st = 0; par ^= 1; }
+                    }
                 }
             }
         }
@@ -2170,24 +1426,32 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             const uint32_t elected = elect_one();
             const int c = warp - 16;
             const uint32_t s0 = smem_u32(smem);
-            uint64_t* b = &bars[16 * c];
+            uint64_t* b = &bars[8 * c];
             const uint32_t dg = tmem + c * 256, dc = dg + 2 * kH, ta = dg + 3 * kH;
             const int total = tiles_of(c) * kWindow;
-            uint32_t cn = 0;
+            const int total1 = tiles_of(1) * kWindow;
             mbar_wait(w_bar, 0);
             for (int gs = 0; gs < total; ++gs) {
                 const uint32_t par = gs & 1;
+                // this step's chunks in the shared ring: entries are ordered (step, chain), chain 1 stops at total1
+                uint32_t cn = (uint32_t)(c == 0 ? gs + (gs < total1 ? gs : total1) : 2 * gs + 1) * Cfg::kChunks;
+                // An mbarrier wait only tells phases apart by parity, so a consumer must never look at a stage two
+                // uses ahead of it: the issuers take their ring entries strictly in turn - this one starts after the
+                // other chain's issuer has passed the full-waits of the entry before.
+                if (c == 1) mbar_wait(&bars[Cfg::kBarXdone], gs & 1);
+                else if (gs > 0 && gs - 1 < total1) mbar_wait(&bars[8 + Cfg::kBarXdone], (gs - 1) & 1);
                 // x part: needs the previous step's accumulators drained
                 if (gs > 0) mbar_wait(&b[Cfg::kBarCfree], (gs - 1) & 1);
                 if (lane == 0) CF_TR(c, gs, 10);
                 for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
-                    const int st = cn % Cfg::kStages;
-                    mbar_wait(&b[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
+                    const uint32_t st = cn % Cfg::kStages;
+                    mbar_wait(&bars[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
                     tc_fence_after_sync();
-                    const uint32_t a0 = s0 + Cfg::kRing + (c * Cfg::kStages + st) * 8192;
+                    const uint32_t a0 = s0 + Cfg::kRing + st * 8192;
                     if (kE5) {
                         const uint32_t wx = s0 + Cfg::kWx + kk * 2 * (kNX * 16);
                         umma_bf16_pred(dg, make_smem_desc(a0, 2048, 128), make_smem_desc(wx, kNX * 16, 128), idesc_x, kk != 0, elected);
+                        if (!(kExp & 2))
                         umma_f8_pred(dg, make_smem_desc(a0 + 4096u, 2048, 128),
                                      make_smem_desc(wx + (uint32_t)KX * kNX * 2, kNX * 16, 128), idesc_x8, 1, elected);
                     } else {
@@ -2198,9 +1462,10 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                             umma_bf16_pred(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0, elected);
                         }
                     }
-                    umma_commit_pred(&b[Cfg::kBarEmpty + st], elected);
+                    umma_commit_pred(&bars[Cfg::kBarEmpty + st], elected);
                     if (lane == 0) CF_TR(c, gs, 20 + kk);
                 }
+                if (lane == 0) mbar_arrive(&b[Cfg::kBarXdone]);
                 // state part of the gates
                 mbar_wait(&b[Cfg::kBarH], par);
                 if (lane == 0) CF_TR(c, gs, 30);
@@ -2210,6 +1475,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     for (int kk = 0; kk < kH / 16; ++kk) {
                         const uint32_t wp = s0 + Cfg::kWgh + kk * 2 * (128 * 16);
                         umma_bf16_ts_pred(dg, ta + kk * 8, make_smem_desc(wp, 128 * 16, 128), idesc_g, 1, elected);
+                        if (!(kExp & 2))
                         umma_f8_ts_pred(dg, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 128 * 2, 128 * 16, 128), idesc_g8, 1, elected);
                     }
                 } else {
@@ -2233,6 +1499,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     for (int kk = 0; kk < kH / 16; ++kk) {
                         const uint32_t wp = s0 + Cfg::kWch + kk * 2 * (64 * 16);
                         umma_bf16_ts_pred(dc, ta + kk * 8, make_smem_desc(wp, 64 * 16, 128), idesc_c, 1, elected);
+                        if (!(kExp & 2))
                         umma_f8_ts_pred(dc, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 64 * 2, 64 * 16, 128), idesc_c8, 1, elected);
                     }
                 } else {
@@ -2255,7 +1522,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         const int q = warp & 3, hf = (warp >> 2) & 1;
         const int row = q * 32 + lane;
         const int j0 = hf * 32;
-        uint64_t* b = &bars[16 * chain];
+        uint64_t* b = &bars[8 * chain];
         const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + chain * 256 + j0;          // + gate * 64 + c0
         const uint32_t t_ahi = tmem + ((uint32_t)(q * 32) << 16) + chain * 256 + 3 * kH + j0 / 2;   // + c0 / 2
         const uint32_t t_alo = t_ahi + 32;
@@ -2397,7 +1664,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
                 }
                 if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 55);
-                if (y_out) {
+                if (y_out && !(kExp & 4)) {
                     // next layer's A operand: block {plane 0, plane 1} x [16][128][8], features dir*64 + j,
                     // in the NEXT layer's operand format (a second split when it differs from this layer's)
                     if (FMT_OUT != FMT) {
@@ -2416,6 +1683,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #pragma unroll
                     for (int kg = 0; kg < 4; ++kg) {
                         *reinterpret_cast<uint4*>(yb + kg * 128 * 8) = make_uint4(hi[4 * kg], hi[4 * kg + 1], hi[4 * kg + 2], hi[4 * kg + 3]);
+                        if (!(kExp & 16) || (kg & 1) == 0)
                         *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + kg * 128 * 8) = make_uint4(lo[4 * kg], lo[4 * kg + 1], lo[4 * kg + 2], lo[4 * kg + 3]);
                     }
                 }
@@ -2542,18 +1810,13 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<32>::kSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruFusedCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv3Smem));
         CF_CUDA(cudaFuncSetAttribute(tc_conv4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv4Smem));
-        CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
-        CF_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
         e->attr_done = true;
     }
     const int64_t chunk = n_tiles < kTcChunkTiles ? n_tiles : kTcChunkTiles;
@@ -2581,25 +1844,12 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         if (e->conv_params) {
             ProfScope ps(prof, KC_K2_CONV, stream);
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
-            if (e->conv_variant == 4 && e->conv_nres == 2) {
+            if (e->conv_nres == 2)
                 tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                      tab.read, tile0, (int)tiles, a0);
-            } else if (e->conv_variant >= 3 && e->conv_nres == 2) {
-                tc_conv3_kernel<<<grid, 576, kConv3Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                  tab.read, tile0, (int)tiles, a0);
-            } else if (e->conv_variant >= 2) {
-                if (e->conv_nres == 2)
-                    tc_conv2_kernel<2><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0);
-                else
-                    tc_conv2_kernel<1><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                         tab.read, tile0, (int)tiles, a0);
-            } else if (e->conv_nres == 2)
-                tc_conv_kernel<2><<<grid, 128, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                    tab.read, tile0, (int)tiles, a0);
             else
-                tc_conv_kernel<1><<<grid, 128, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                    tab.read, tile0, (int)tiles, a0);
+                tc_conv2_kernel<1><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
+                                                                     tab.read, tile0, (int)tiles, a0);
             CF_LAUNCHED();
             a_in = a0;
         } else {
@@ -2620,61 +1870,48 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     a_in = a0;
                 }
                 ProfScope ps(prof, KC_K4_GRU, stream);
-                if (e->fused_variant == 2) {
-                    long long* trace_dev = nullptr;
-                    if (getenv("CF_TC_TRACE") && !e->trace_done && L.in != kC) {
-                        CF_CUDA(cudaMalloc(&trace_dev, 5 * 200 * 2 * sizeof(long long)));
-                        CF_CUDA(cudaMemsetAsync(trace_dev, 0, 5 * 200 * 2 * sizeof(long long), stream));
-                    }
-                    const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
-                    const float* hw_l = last ? e->head_w : nullptr;
-                    float* hp_l = last ? head_part : nullptr;
-                    // operand format of this layer and of the layer that reads its output
-                    const int fmt_out = last ? L.fmt : e->layers[l + 1].fmt;
-                    if (L.in == kC) {
-                        if (fmt_out == kFmtF16E5)
-                            tc_gru_fused2_kernel<32, 0, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
-                        else
-                            tc_gru_fused2_kernel<32, 0, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
-                                L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, nullptr);
-                    } else if (L.fmt == kFmtF16E5) {
-                        tc_gru_fused2_kernel<128, 1, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
-                    } else {
-                        tc_gru_fused2_kernel<128, 0, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, e->x_depth, trace_dev);
-                    }
-                    CF_LAUNCHED();
-                    if (trace_dev) {
-                        // debug: dump the timeline of block 0 and stop tracing
-                        CF_CUDA(cudaStreamSynchronize(stream));
-                        std::vector<long long> host(5 * 200 * 2);
-                        CF_CUDA(cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-                        if (FILE* f = fopen(getenv("CF_TC_TRACE"), "w")) {
-                            for (int rg = 0; rg < 5; ++rg)
-                                for (int k = 0; k < 200; ++k)
-                                    if (host[(rg * 200 + k) * 2 + 1])
-                                        fprintf(f, "%d %lld %lld\n", rg, host[(rg * 200 + k) * 2], host[(rg * 200 + k) * 2 + 1]);
-                            fclose(f);
-                        }
-                        cudaFree(trace_dev);
-                        e->trace_done = true;
-                    }
-                    a_in = yo;
-                    head_parts = 4;
-                    continue;
+                long long* trace_dev = nullptr;
+                if (e->trace_path && !e->trace_done && L.in != kC) {
+                    CF_CUDA(cudaMalloc(&trace_dev, 5 * 200 * 2 * sizeof(long long)));
+                    CF_CUDA(cudaMemsetAsync(trace_dev, 0, 5 * 200 * 2 * sizeof(long long), stream));
                 }
-                const int grid = 2 * (int)std::min<int64_t>(tiles, e->n_sms / 2);
-                if (L.in == kC)
-                    tc_gru_fused_kernel<32><<<grid, 576, GruFusedCfg<32>::kSmem, stream>>>(
-                        L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->dbg);
-                else
-                    tc_gru_fused_kernel<128><<<grid, 576, GruFusedCfg<128>::kSmem, stream>>>(
-                        L.wfused, L.bz, a_in, yo, last ? e->head_w : nullptr, last ? head_part : nullptr, (int)tiles, e->dbg);
+                const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
+                const float* hw_l = last ? e->head_w : nullptr;
+                float* hp_l = last ? head_part : nullptr;
+                // operand format of this layer and of the layer that reads its output
+                const int fmt_out = last ? L.fmt : e->layers[l + 1].fmt;
+                if (L.in == kC) {
+                    if (fmt_out == kFmtF16E5)
+                        tc_gru_fused2_kernel<32, 0, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr);
+                    else
+                        tc_gru_fused2_kernel<32, 0, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr);
+                } else if (L.fmt == kFmtF16E5) {
+                    tc_gru_fused2_kernel<128, 1, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                        L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev);
+                } else {
+                    tc_gru_fused2_kernel<128, 0, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                        L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev);
+                }
                 CF_LAUNCHED();
+                if (trace_dev) {
+                    // debug (CF_TC_TRACE=<file>): dump the timeline of block 0 once; results are unaffected
+                    CF_CUDA(cudaStreamSynchronize(stream));
+                    std::vector<long long> host(5 * 200 * 2);
+                    CF_CUDA(cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                    if (FILE* f = fopen(e->trace_path, "w")) {
+                        for (int rg = 0; rg < 5; ++rg)
+                            for (int k = 0; k < 200; ++k)
+                                if (host[(rg * 200 + k) * 2 + 1])
+                                    fprintf(f, "%d %lld %lld\n", rg, host[(rg * 200 + k) * 2], host[(rg * 200 + k) * 2 + 1]);
+                        fclose(f);
+                    }
+                    cudaFree(trace_dev);
+                    e->trace_done = true;
+                }
                 a_in = yo;
-                head_parts = 8;
+                head_parts = 4;
                 continue;
             }
             head_parts = 2;

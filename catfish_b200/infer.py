@@ -20,12 +20,69 @@ correct_short :174            correct_short               cf_correct_short
 PyTorch tensors are used only to hold device buffers and to name the stream.
 """
 
+import collections.abc
 import ctypes
 import os
 
 import numpy as np
 
 from . import _cabi
+
+_STAGING = {}        # device index -> pinned int16 torch tensor the ragged batch is concatenated into
+
+
+class IntervalList(collections.abc.Sequence):
+    """The ``[[start, end], ...]`` list of one read (infer.py:149-162), backed by the int64 [n, 2] slice of the
+    batch result.  Behaves like the reference's list of two-element lists of Python ints (indexing, iteration,
+    ``len``, ``==`` with a list), but the Python objects are only built when asked for: a 512-read batch holds
+    ~3e5 intervals and eager conversion costs more than the GPU work of the whole batch."""
+
+    __slots__ = ("array",)
+
+    def __init__(self, array):
+        self.array = array
+
+    def __len__(self):
+        return int(self.array.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self.array[i].tolist()
+        return self.array[i].tolist()
+
+    def __iter__(self):
+        return iter(self.array.tolist())
+
+    def __eq__(self, other):
+        if isinstance(other, IntervalList):
+            return np.array_equal(self.array, other.array)
+        if isinstance(other, (list, tuple)):
+            return self.array.tolist() == [list(x) if isinstance(x, tuple) else x for x in other]
+        return NotImplemented
+
+    def __ne__(self, other):
+        r = self.__eq__(other)
+        return r if r is NotImplemented else not r
+
+    __hash__ = None
+
+    def tolist(self):
+        return self.array.tolist()
+
+    def __repr__(self):
+        return repr(self.array.tolist())
+
+    def __reduce__(self):
+        return (IntervalList, (np.ascontiguousarray(self.array),))
+
+
+def _staging(torch, device, n):
+    """Pinned host buffer of at least n int16 samples for `device` (grows geometrically, reused across calls)."""
+    buf = _STAGING.get(device)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n + n // 4, 1 << 20), dtype=torch.int16).pin_memory()
+        _STAGING[device] = buf
+    return buf
 
 
 def _torch():
@@ -59,18 +116,19 @@ def infer_class_from_raw(raw, model, label=1, window_size=35, threshold=0.5):
     """Array-level twin of infer_class_from_signal: ``raw`` is the int16 signal of one read
     with the leading ``first_sample_template`` samples already dropped (infer.py:87-90)."""
     hps, lengths = infer_reads([raw], model, threshold=threshold, window_size=window_size)
-    return hps[0], lengths[0]
+    return hps[0].tolist(), lengths[0]          # a plain list of [int, int], exactly the reference's type
 
 
 def infer_reads(raws, model, threshold=0.5, min_run=15, extension_left=11, extension_right=16,
                 window_size=35, return_scores=False):
     """Batched infer_class_from_signal over a list of int16 reads (ragged).
 
-    Returns ``(hps, lengths)`` - per read the list of [start, end] intervals (Python ints, as the
-    reference) and ``len(labels)`` - plus the per-position float32 scores when
+    Returns ``(hps, lengths)`` - per read the [start, end] intervals (an ``IntervalList``: list-like, Python
+    ints on access, as the reference) and ``len(labels)`` - plus the per-position float32 scores when
     ``return_scores`` is set.  One C-ABI call: host->device copy of the signal, median/MAD
     normalisation, windowing, network, threshold / short-run removal / interval emission,
-    device->host copy of the results."""
+    device->host copy of the results.  The ragged batch is concatenated straight into a pinned staging
+    buffer (one host pass, then DMA at PCIe rate instead of a pageable copy)."""
     if window_size != model.window:
         raise ValueError("window_size must equal the model's window (%d)" % model.window)
     arrays = [_as_int16(r) for r in raws]
@@ -81,13 +139,19 @@ def infer_reads(raws, model, threshold=0.5, min_run=15, extension_left=11, exten
     offsets = np.zeros(n_reads + 1, np.int64)
     if n_reads:
         offsets[1:] = np.cumsum([a.size for a in arrays])
-    raw = np.concatenate(arrays) if n_reads else np.zeros(0, np.int16)
+    total = int(offsets[-1])
+    if n_reads:
+        stage = _staging(_torch(), int(model.device), total).numpy()[:total]
+        np.concatenate(arrays, out=stage)
+        raw = stage
+    else:
+        raw = np.zeros(0, np.int16)
     res = infer_concatenated(raw, offsets, model, threshold, min_run, extension_left, extension_right,
                              return_scores)
     intervals, ioff = res[0], res[1]
     lengths = [int(a.size) for a in arrays]
-    pairs = intervals.tolist()
-    hps = [pairs[int(ioff[r]):int(ioff[r + 1])] for r in range(n_reads)]
+    bounds = ioff.tolist()
+    hps = [IntervalList(intervals[bounds[r]:bounds[r + 1]]) for r in range(n_reads)]
     if return_scores:
         scores = [res[2][int(offsets[r]):int(offsets[r + 1])] for r in range(n_reads)]
         return hps, lengths, scores

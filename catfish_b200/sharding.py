@@ -55,12 +55,47 @@ def gather_results(local_indices, local_results, n_reads, rank, world_size, dst=
     return out
 
 
-def infer_reads_sharded(raws, model, rank, world_size, **kwargs):
-    """``infer.infer_reads`` over this rank's shard; (hps, lengths) for all reads on rank 0."""
+def gather_intervals(local_indices, local_hps, local_lengths, n_reads, rank, world_size, dst=0):
+    """Host-side gather of per-read interval lists in compact form: every rank sends ONE tuple of numpy arrays
+    (read indices, read lengths, CSR offsets, intervals [n, 2]) instead of one Python object per interval, and
+    rank ``dst`` rebuilds the per-read ``IntervalList`` views.  Returns (hps, lengths) in read order on ``dst``."""
+    from .infer import IntervalList
+    counts = np.array([len(h) for h in local_hps], np.int64)
+    ioff = np.zeros(len(local_hps) + 1, np.int64)
+    np.cumsum(counts, out=ioff[1:])
+    if len(local_hps):
+        flat = np.concatenate([np.asarray(getattr(h, "array", h), np.int64).reshape(-1, 2) for h in local_hps])
+    else:
+        flat = np.zeros((0, 2), np.int64)
+    payload = (np.asarray(local_indices, np.int64), np.asarray(local_lengths, np.int64), ioff, flat)
+    if world_size == 1:
+        gathered = [payload]
+    else:
+        import torch.distributed as dist
+        gathered = [None] * world_size if rank == dst else None
+        dist.gather_object(payload, gathered, dst=dst)
+        if rank != dst:
+            return None
+    hps = [None] * n_reads
+    lengths = [None] * n_reads
+    for idx, lens, off, iv in gathered:
+        bounds = off.tolist()
+        for k, i in enumerate(idx.tolist()):
+            hps[i] = IntervalList(iv[bounds[k]:bounds[k + 1]])
+            lengths[i] = int(lens[k])
+    return hps, lengths
+
+
+def infer_reads_sharded(raws, model, rank, world_size, batch_reads=512, **kwargs):
+    """The reference's loop over all reads (catfish/catfish:55-56) sharded by read over ``world_size`` GPUs:
+    this rank runs ``infer.infer_reads`` over its LPT shard in batches of ``batch_reads`` reads; (hps, lengths)
+    for ALL reads, in read order, on rank 0 (None elsewhere).  ``raws[i]`` is only touched for reads of this
+    rank's shard, so a caller may pass a lazy sequence."""
     from . import infer
     idx = shard_for_rank([len(r) for r in raws], rank, world_size)
-    hps, lengths = infer.infer_reads([raws[int(i)] for i in idx], model, **kwargs) if len(idx) else ([], [])
-    merged = gather_results(idx, list(zip(hps, lengths)), len(raws), rank, world_size)
-    if merged is None:
-        return None
-    return [m[0] for m in merged], [m[1] for m in merged]
+    hps, lengths = [], []
+    for b in range(0, len(idx), batch_reads):
+        h, l = infer.infer_reads([raws[int(i)] for i in idx[b:b + batch_reads]], model, **kwargs)
+        hps.extend(h)
+        lengths.extend(l)
+    return gather_intervals(idx, hps, lengths, len(raws), rank, world_size)

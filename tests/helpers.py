@@ -46,3 +46,51 @@ def random_labels(rng, n, p_switch=0.08):
 def allowed_label_flips(p_ref, threshold=0.5, band=1e-3):
     """Positions where the contract allows a different label: reference p within `band` of the threshold."""
     return np.abs(np.asarray(p_ref, np.float64) - threshold) <= band
+
+
+class FakeFast5(object):
+    """In-memory stand-in for an open ``h5py.File`` with the three things infer.py:87-90 touches: the
+    ``first_sample_template`` attribute of the segmentation summary, ``Raw/Reads/`` with ``visit`` (h5py calls
+    the function on every member name and returns its first non-None result) and the ``Signal`` dataset."""
+
+    class _Node(object):
+        def __init__(self, attrs=None, members=None, data=None):
+            self.attrs = attrs or {}
+            self._members = members or []
+            self._data = data
+
+        def visit(self, func):
+            for name in self._members:
+                out = func(name)
+                if out is not None:
+                    return out
+            return None
+
+        def __getitem__(self, key):
+            assert key == ()
+            return self._data
+
+    def __init__(self, signal, first_sample, read_names=("Read_117",)):
+        self.signal = np.asarray(signal, np.int16)
+        self.nodes = {
+            "Analyses/Segmentation_000/Summary/segmentation": self._Node(attrs={"first_sample_template": first_sample}),
+            "Raw/Reads/": self._Node(members=list(read_names)),
+            "Raw/Reads/%s/Signal" % read_names[0]: self._Node(data=self.signal),
+        }
+
+    def __getitem__(self, path):
+        return self.nodes[path]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def fake_h5py_module(files):
+    """A module object to put into ``sys.modules['h5py']``: ``File(path, mode)`` returns ``files[path]``."""
+    import types
+    mod = types.ModuleType("h5py")
+    mod.File = lambda path, mode="r": files[path]
+    return mod

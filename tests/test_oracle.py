@@ -5,7 +5,7 @@ import pytest
 import os
 import sys
 
-from helpers import golden, hpm_from_golden, random_bn_weights, random_labels
+from helpers import FakeFast5, golden, hpm_from_golden, random_bn_weights, random_labels
 from catfish_b200 import synth, weights
 from oracle import postprocess, ref_infer, tf_graph, validation
 
@@ -205,3 +205,19 @@ def test_gru_is_reset_before_matmul():
     out = tf_graph._gru_direction_np(x.astype(float), w, pre, False)
     np.testing.assert_allclose(out[0, 0], h1, atol=1e-12)
     assert p.shape == (70,)
+
+
+@needs_ref
+def test_fast5_trimming_matches_reference_process_signal():
+    """process_signal (infer.py:77-93) run by the REFERENCE's own function on an in-memory FAST5 stand-in equals
+    the product's host-side trimming (`_trimmed_raw`: first_sample_template, first Raw/Reads member) followed by
+    the oracle's normalisation."""
+    from catfish_b200 import infer as product_infer
+    ref = ref_infer.load()
+    for n, first in ((900, 0), (900, 137), (36, 1)):
+        f = FakeFast5(synth.synth_read(n, 40 + n + first), first, read_names=("Read_5", "Read_9"))
+        want = ref.process_signal(f, "median")
+        trimmed = product_infer._trimmed_raw(f)
+        assert trimmed.dtype == np.int16 and len(trimmed) == n - first
+        np.testing.assert_array_equal(trimmed, f.signal[first:])
+        np.testing.assert_array_equal(postprocess.normalize_raw_signal(trimmed), want)

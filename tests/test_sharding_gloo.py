@@ -29,10 +29,16 @@ def _worker(rank, world, port, q):
     idx = sharding.shard_for_rank(lengths, rank, world)
     local = [_fake_infer(reads[int(i)]) for i in idx]
     merged = sharding.gather_results(idx, local, len(reads), rank, world)
+    # the compact path the sharded job uses: one tuple of arrays per rank, IntervalList views on rank 0
+    hps = [np.array([[int(r[0]), k] for k in range(int(r[1]) % 4)], np.int64).reshape(-1, 2) for r in (reads[int(i)] for i in idx)]
+    compact = sharding.gather_intervals(idx, hps, [len(reads[int(i)]) for i in idx], len(reads), rank, world)
     if rank == 0:
+        want_hps = [[[int(r[0]), k] for k in range(int(r[1]) % 4)] for r in reads]
+        assert [h.tolist() for h in compact[0]] == want_hps and compact[1] == [len(r) for r in reads]
+        assert all(h == w for h, w in zip(compact[0], want_hps))          # list-like equality of IntervalList
         q.put((merged, [_fake_infer(r) for r in reads], [int(lengths[p].sum()) for p in sharding.partition_reads(lengths, world)]))
     else:
-        assert merged is None
+        assert merged is None and compact is None
     dist.barrier()
     dist.destroy_process_group()
 
