@@ -26,6 +26,7 @@
 // block is one contiguous cp.async.bulk (TMA) copy.  xp is stored per block as [384][128] fp32
 // (column-major), which makes both its producer (TMEM lane = window) and its consumer coalesced.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -83,10 +84,10 @@ static void pack_b_operand(const float* w, int K, int N, int ldw, int col0, std:
         }
 }
 
-// B operand in the "f16e5" format (tc_ptx.cuh): plane 0 = fp16 [K/8][N][8]; plane 1 = e5m2
-// [2K/16][N][16]: per chunk of 16 K-rows first the 16 fp16 parts / S, then the 16 remainders * S -
-// the K' order the A-side producers use.  Same byte count and the same per-chunk descriptor offsets
-// as the split-bf16 layout.
+// B operand in the "f16e5" format (tc_ptx.cuh): plane 0 = fp16(S w_h) [K/8][N][8] (the A side stores
+// a_h / S); plane 1 = e5m2 [2K/16][N][16]: per chunk of 16 K-rows first the 16 fp16 parts / S, then the
+// 16 remainders * S - the K' order the A-side producers use.  Same byte count and the same per-chunk
+// descriptor offsets as the split-bf16 layout.  Needs |w| < 65504 / S (tc_create checks).
 static void pack_b_operand_f16e5(const float* w, int K, int N, int ldw, int col0, std::vector<__nv_bfloat16>* out,
                                  float scale = 1.f, int n_split = 1 << 30, float scale_hi = 1.f) {
     const size_t plane = (size_t)K * N;
@@ -99,7 +100,8 @@ static void pack_b_operand_f16e5(const float* w, int K, int N, int ldw, int col0
             const float v = w[(size_t)k * ldw + col0 + n] * (n < n_split ? scale : scale_hi);
             const __half h = __float2half_rn(v);
             const float hf = __half2float(h);
-            main[((size_t)(k / 8) * N + n) * 8 + (k % 8)] = *reinterpret_cast<const uint16_t*>(&h);
+            const __half hs = __float2half_rn(hf * kCorrScale);          // exact: a power-of-two scale
+            main[((size_t)(k / 8) * N + n) * 8 + (k % 8)] = *reinterpret_cast<const uint16_t*>(&hs);
             const int c = k / 16, kc = k % 16;
             corr[((size_t)(2 * c) * N + n) * 16 + kc] = (uint8_t)__nv_cvt_float_to_fp8(hf / kCorrScale, __NV_SATFINITE, __NV_E5M2);
             corr[((size_t)(2 * c + 1) * N + n) * 16 + kc] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * kCorrScale, __NV_SATFINITE, __NV_E5M2);
@@ -167,7 +169,14 @@ TcEngine* tc_create(const HostModel& hm) {
         const bool covered = hm.desc.network_type == CF_NET_RESNET_RNN && hm.n_res() == 2 && hm.conv_channels() == kC &&
                              e->use_fused;
         const char* env = getenv("CF_TC_FMT");
-        e->fmt = covered && !(env && env[0] == '0') ? kFmtF16E5 : kFmtBf16x3;
+        float wmax = 0.f;                             // the fp16 weight plane is stored times S = 64
+        for (const GruDir& g : hm.gru) {
+            for (float v : g.wx) wmax = std::max(wmax, std::fabs(v));
+            for (float v : g.wgh) wmax = std::max(wmax, std::fabs(v));
+            for (float v : g.wch) wmax = std::max(wmax, std::fabs(v));
+        }
+        const bool in_range = wmax * kCandScale * kCorrScale < 60000.f;
+        e->fmt = covered && in_range && !(env && env[0] == '0') ? kFmtF16E5 : kFmtBf16x3;
     }
     if (hm.n_res() >= 1 && hm.n_res() <= 2 && hm.conv_channels() == kC) {
         // TK2 parameter block: fp32 vectors, then the B operands in the given format (see ConvParams)
@@ -561,11 +570,11 @@ __device__ __forceinline__ void split4(float v0, float v1, float v2, float v3, i
         split_bf16x2(v0, v1, m8[i >> 1], s8[i >> 1]);
         split_bf16x2(v2, v3, m8[(i >> 1) + 1], s8[(i >> 1) + 1]);
     } else {
-        uint32_t la, ha, lb, hb;
-        split_f16e5x2(v0, v1, m8[i >> 1], la, ha);
-        split_f16e5x2(v2, v3, m8[(i >> 1) + 1], lb, hb);
+        uint32_t la, lb;
+        split_f16e5x2(v0, v1, m8[i >> 1], la);
+        split_f16e5x2(v2, v3, m8[(i >> 1) + 1], lb);
         s8[i >> 2] = la | (lb << 16);
-        s8[4 + (i >> 2)] = ha | (hb << 16);
+        s8[4 + (i >> 2)] = f16e5_hi4(m8[i >> 1], m8[(i >> 1) + 1]);
     }
 }
 
@@ -1296,6 +1305,8 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
 //   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
 //   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
 //   warp 18          : lane 0 = producer (weights once, then the x ring)
+//   warp 19          : f16e5 input only - rebuilds each landed chunk's hi-byte slab from its main plane (the
+//                      compact HBM form carries 3 of the 4 operand bytes; tc_ptx.cuh) and hands the stage on
 template <int KX> struct GruF2Cfg {
     static constexpr int kChunks = KX / 16;
     static constexpr int kStages = 10;                                    // ONE ring shared by both chains (see the producer)
@@ -1309,11 +1320,15 @@ template <int KX> struct GruF2Cfg {
     static constexpr uint32_t kSmem = kBars + 512;
     // barriers: a chain's group of 8, then the ring's full / empty pairs, then the weight barrier
     static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarXdone = 5;
-    static constexpr int kBarFull = 16, kBarEmpty = 16 + kStages, kBarW = 16 + 2 * kStages;
+    static constexpr int kBarFull = 16, kBarEmpty = 16 + kStages, kBarTma = 16 + 2 * kStages, kBarW = 16 + 3 * kStages;
 };
+// Bytes of one (tile, t) block of a 128-wide layer output in HBM: split bf16 = two 16-bit planes; f16e5 =
+// fp16 main plane [16][128][8 x 2 B] + remainder bytes [8 chunks][128][16 B] (the hi bytes are rebuilt by the reader).
+__host__ __device__ constexpr uint32_t gru_out_block_bytes(int fmt) { return fmt == kFmtF16E5 ? 49152u : 65536u; }
+constexpr int kGruF2Threads = 640;
 
 template <int KX, int FMT, int FMT_OUT>
-__global__ void __launch_bounds__(608, 1)
+__global__ void __launch_bounds__(kGruF2Threads, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
                      const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles,
@@ -1360,7 +1375,11 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             mbar_init(&b[Cfg::kBarCfree], 8);
             mbar_init(&b[Cfg::kBarXdone], 1);
         }
-        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&bars[Cfg::kBarFull + i], 1); mbar_init(&bars[Cfg::kBarEmpty + i], 1); }
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(&bars[Cfg::kBarFull + i], 1);
+            mbar_init(&bars[Cfg::kBarEmpty + i], 1);
+            mbar_init(&bars[Cfg::kBarTma + i], 1);
+        }
         mbar_init(w_bar, 1);
         fence_mbar_init();
     }
@@ -1385,34 +1404,61 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 const uint32_t n = Cfg::kWBytes - off < 32768 ? Cfg::kWBytes - off : 32768;
                 bulk_g2s(smem + off, wsrc + off, n, w_bar);
             }
+            // input block in HBM: split bf16 = two planes of 128 * KX * 2 bytes; compact f16e5 = main plane + KX / 16
+            // remainder slabs of 2 KB (the chunk's hi slab, the last 2 KB of the stage, is filled by warp 19)
+            constexpr bool kCompact = FMT == kFmtF16E5;
             constexpr size_t plane = (size_t)128 * KX * 2;
+            constexpr size_t blk_bytes = kCompact ? plane + (size_t)(KX / 16) * 2048 : 2 * plane;
             const uint8_t* xbase = reinterpret_cast<const uint8_t*>(x_blocks);
             const int total0 = tiles_of(0) * kWindow, total1 = tiles_of(1) * kWindow;     // total1 <= total0
             uint32_t st = 0, par = 1;                     // ring position; parity of the empty barrier's previous phase
             for (int gs = 0; gs < total0; ++gs) {
                 for (int c = 0; c < 2; ++c) {
                     if (c == 1 && gs >= total1) break;
-                    const uint8_t* xb = xbase + blk_of(c, gs) * 2 * plane;
+                    const uint8_t* xb = xbase + blk_of(c, gs) * blk_bytes;
                     for (int kk = 0; kk < Cfg::kChunks; ++kk) {
                         mbar_wait(&bars[Cfg::kBarEmpty + st], par);
                         uint8_t* dst = smem + Cfg::kRing + st * 8192;
-                        if (kExp & 1) { mbar_arrive(&bars[Cfg::kBarFull + st]); if (++st == Cfg::kStages) { st = 0; par ^= 1; } continue; }
-                        if (kExp & 16) {      // timing experiment: three quarters of the bytes
-                            mbar_expect_tx(&bars[Cfg::kBarFull + st], 6144);
-                            bulk_g2s(dst, xb + kk * 4096, 4096, &bars[Cfg::kBarFull + st]);
-                            bulk_g2s(dst + 4096, xb + plane + kk * 4096, 2048, &bars[Cfg::kBarFull + st]);
-                            if (++st == Cfg::kStages) { st = 0; par ^= 1; }
-                            continue;
+                        uint64_t* landed = &bars[(kCompact ? Cfg::kBarTma : Cfg::kBarFull) + st];
+                        if (kExp & 1) { mbar_arrive(landed); if (++st == Cfg::kStages) { st = 0; par ^= 1; } continue; }
+                        if (kCompact) {
+                            mbar_expect_tx(landed, 6144);
+                            bulk_g2s(dst, xb + kk * 4096, 4096, landed);
+                            bulk_g2s(dst + 4096, xb + plane + kk * 2048, 2048, landed);
+                        } else {
+                            mbar_expect_tx(landed, 8192);
+                            bulk_g2s(dst, xb + kk * 4096, 4096, landed);
+                            bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, landed);
                         }
-                        mbar_expect_tx(&bars[Cfg::kBarFull + st], 8192);
-                        bulk_g2s(dst, xb + kk * 4096, 4096, &bars[Cfg::kBarFull + st]);
-                        bulk_g2s(dst + 4096, xb + plane + kk * 4096, 4096, &bars[Cfg::kBarFull + st]);
                         if (++st == Cfg::kStages) { st = 0; par ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp >= 16) {
+    } else if (warp == 19) {
+        // ------------------------------------------------------------ hi-byte slab of every landed chunk (f16e5 input)
+        if (FMT == kFmtF16E5) {
+            const int total0 = tiles_of(0) * kWindow, total1 = tiles_of(1) * kWindow;
+            const int n_chunks = (total0 + total1) * Cfg::kChunks;
+            uint32_t st = 0, par = 0;
+            for (int cn = 0; cn < n_chunks; ++cn) {
+                mbar_wait(&bars[Cfg::kBarTma + st], par);
+                uint8_t* stage = smem + Cfg::kRing + st * 8192;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int row = r * 32 + lane;
+                    const uint4 a = *reinterpret_cast<const uint4*>(stage + row * 16);            // K 0..7 of the chunk
+                    const uint4 b = *reinterpret_cast<const uint4*>(stage + 2048 + row * 16);     // K 8..15
+                    *reinterpret_cast<uint4*>(stage + 6144 + row * 16) =
+                        make_uint4(f16e5_hi4(a.x, a.y), f16e5_hi4(a.z, a.w), f16e5_hi4(b.x, b.y), f16e5_hi4(b.z, b.w));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[Cfg::kBarFull + st]);
+                if (++st == Cfg::kStages) { st = 0; par ^= 1; }
+            }
+        }
+    } else if (warp >= 16 && warp < 18) {
         // ------------------------------------------------------------ MMA issuer of chain (warp - 16)
         // Warp-converged: all lanes run the control flow and the waits, one elected lane issues
         // (descriptor arithmetic stays on the uniform datapath: ~10 instead of ~80 cycles per MMA).
@@ -1679,12 +1725,23 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                             split4<FMT_OUT>(h[i], h[i + 1], h[i + 2], h[i + 3], i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
 #endif
                     }
-                    __nv_bfloat16* yb = y_out + blk * (2 * 128 * 2 * kH) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 8;
+                    // hi[] = main words of the 32 values; lo[] = per 16 values: 4 words of remainder bytes, then the 4
+                    // words of hi bytes (f16e5) / 8 words of bf16 remainders (split bf16)
+                    uint8_t* yb = reinterpret_cast<uint8_t*>(y_out) + blk * gru_out_block_bytes(FMT_OUT);
+                    uint8_t* ym = yb + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 16;
 #pragma unroll
-                    for (int kg = 0; kg < 4; ++kg) {
-                        *reinterpret_cast<uint4*>(yb + kg * 128 * 8) = make_uint4(hi[4 * kg], hi[4 * kg + 1], hi[4 * kg + 2], hi[4 * kg + 3]);
-                        if (!(kExp & 16) || (kg & 1) == 0)
-                        *reinterpret_cast<uint4*>(yb + 128 * 2 * kH + kg * 128 * 8) = make_uint4(lo[4 * kg], lo[4 * kg + 1], lo[4 * kg + 2], lo[4 * kg + 3]);
+                    for (int kg = 0; kg < 4; ++kg)
+                        *reinterpret_cast<uint4*>(ym + kg * 2048) = make_uint4(hi[4 * kg], hi[4 * kg + 1], hi[4 * kg + 2], hi[4 * kg + 3]);
+                    if (FMT_OUT == kFmtF16E5) {
+                        // compact form: only the remainder bytes travel (one 2 KB slab per K = 16 chunk of the block)
+                        uint8_t* yl = yb + 128 * 2 * kH * 2 + ((size_t)(dir * kH + j0) / 16 * 128 + row) * 16;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            *reinterpret_cast<uint4*>(yl + c * 2048) = make_uint4(lo[8 * c], lo[8 * c + 1], lo[8 * c + 2], lo[8 * c + 3]);
+                    } else {
+#pragma unroll
+                        for (int kg = 0; kg < 4; ++kg)
+                            *reinterpret_cast<uint4*>(ym + 128 * 2 * kH * 2 + kg * 2048) = make_uint4(lo[4 * kg], lo[4 * kg + 1], lo[4 * kg + 2], lo[4 * kg + 3]);
                     }
                 }
                 if (head_part) {
@@ -1882,16 +1939,16 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 const int fmt_out = last ? L.fmt : e->layers[l + 1].fmt;
                 if (L.in == kC) {
                     if (fmt_out == kFmtF16E5)
-                        tc_gru_fused2_kernel<32, 0, 1><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                        tc_gru_fused2_kernel<32, 0, 1><<<grid2, kGruF2Threads, GruF2Cfg<32>::kSmem, stream>>>(
                             L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr);
                     else
-                        tc_gru_fused2_kernel<32, 0, 0><<<grid2, 608, GruF2Cfg<32>::kSmem, stream>>>(
+                        tc_gru_fused2_kernel<32, 0, 0><<<grid2, kGruF2Threads, GruF2Cfg<32>::kSmem, stream>>>(
                             L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr);
                 } else if (L.fmt == kFmtF16E5) {
-                    tc_gru_fused2_kernel<128, 1, 1><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                    tc_gru_fused2_kernel<128, 1, 1><<<grid2, kGruF2Threads, GruF2Cfg<128>::kSmem, stream>>>(
                         L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev);
                 } else {
-                    tc_gru_fused2_kernel<128, 0, 0><<<grid2, 608, GruF2Cfg<128>::kSmem, stream>>>(
+                    tc_gru_fused2_kernel<128, 0, 0><<<grid2, kGruF2Threads, GruF2Cfg<128>::kSmem, stream>>>(
                         L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev);
                 }
                 CF_LAUNCHED();

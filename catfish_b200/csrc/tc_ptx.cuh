@@ -312,32 +312,45 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
 // doubled K, at twice the 16-bit rate): the two correction terms are 2^-12 of the product, so the
 // 3 significant bits of e5m2 keep the total near 2^-15; S = 2^6 puts both a_l*S (~2^-12 |a| S) and
 // a_h/S into e5m2's normal range (>= 2^-14) for every |a| >= 2^-8 - smaller values only carry
-// absolute errors below 2^-19 |w|.  Two pass-equivalents instead of the three of bf16x3 (tools/precision_emulation.py:
-// max |dp| 5.6e-5 vs 2.1e-5).
+// absolute errors below 2^-19 |w|.  Two pass-equivalents instead of the three of bf16x3.
+//
+// Storage form of an A operand ("compact": 3 bytes per value in HBM, 4 in shared / tensor memory):
+//   main  m  = fp16(a_h / S)          - the fp16 MMA multiplies it with fp16(S w_h), so the scale cancels
+//   lo byte  = e5m2(a_l * S)          - rounded to nearest
+//   hi byte  = the TOP BYTE of m      - e5m2 has fp16's sign and exponent layout, so the upper byte of an fp16 IS
+//                                       the e5m2 of the same value, truncated to two mantissa bits
+// The hi bytes are a pure byte shuffle of the main plane (one PRMT per four values), so they are never
+// stored in HBM: layer outputs travel as main + lo (3 B / value) and the consumer rebuilds the hi slab
+// in shared memory.  Truncating instead of rounding that byte biases the a_h*w_l correction by at most
+// 2^-3 of a 2^-12 term (emulated end to end: max |dp| 3.4e-5 vs 2.7e-5, tests/tools/precision_emulation.py).
 constexpr float kCorrScale = 64.f;
 // fp16 tops out at 65504 and the corrections need |a| >= 2^-8: the engine uses this format where the
 // activations are GRU states in (-1, 1) (the 128-wide layers); the layer fed by the conv stack, whose
 // activations span 2^-10 .. 60 (and 4.5e5 behind a full-scale spike), stays split bf16.  The fp16
 // conversion saturates rather than produce infinities.
-// Two values -> fp16x2 word (element 0 in the low half), e5m2x2 of the scaled remainders and
-// e5m2x2 of the down-scaled fp16 parts (element 0 in the low byte).
-__device__ __forceinline__ void split_f16e5x2(float x0, float x1, uint32_t& main, uint32_t& lo, uint32_t& hi) {
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(main) : "f"(x1), "f"(x0));   // saturating: no infinities
-    const __half2 h = *reinterpret_cast<const __half2*>(&main);
-    const float2 l = ffma2(__half22float2(h), splat2(-kCorrScale), fmul2(make_float2(x0, x1), splat2(kCorrScale)));
+// Two values -> fp16x2 word of the down-scaled main parts (element 0 in the low half) and the
+// e5m2x2 of the scaled remainders (element 0 in the low byte).
+__device__ __forceinline__ void split_f16e5x2(float x0, float x1, uint32_t& main, uint32_t& lo) {
+    uint32_t h32;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h32) : "f"(x1), "f"(x0));   // saturating: no infinities
+    const __half2 m = __hmul2(*reinterpret_cast<const __half2*>(&h32), __floats2half2_rn(1.f / kCorrScale, 1.f / kCorrScale));
+    main = *reinterpret_cast<const uint32_t*>(&m);
+    // remainder against what the main plane really holds, a_h = S m (below 2^-8 the down-scaled value is an fp16
+    // subnormal and loses bits; the remainder byte picks them up):  S (x - S m) = S x - S^2 m
+    const float2 l = ffma2(__half22float2(m), splat2(-kCorrScale * kCorrScale), fmul2(make_float2(x0, x1), splat2(kCorrScale)));
     lo = __nv_cvt_float2_to_fp8x2(l, __NV_SATFINITE, __NV_E5M2);
-    const __half2 hs = __hmul2(h, __floats2half2_rn(1.f / kCorrScale, 1.f / kCorrScale));
-    hi = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E5M2);
 }
-// 16 values (one K = 16 chunk of an operand row): 8 fp16x2 words + 16 remainder bytes + 16 fp16-part bytes
+// hi bytes of four consecutive values from their two main words
+__device__ __forceinline__ uint32_t f16e5_hi4(uint32_t m01, uint32_t m23) { return __byte_perm(m01, m23, 0x7531); }
+// 16 values (one K = 16 chunk of an operand row): 8 fp16x2 words + 16 remainder bytes + 16 hi bytes
 __device__ __forceinline__ void split_f16e5_chunk(const float* v, uint32_t* main, uint32_t* lo4, uint32_t* hi4) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t la, ha, lb, hb;
-        split_f16e5x2(v[4 * j], v[4 * j + 1], main[2 * j], la, ha);
-        split_f16e5x2(v[4 * j + 2], v[4 * j + 3], main[2 * j + 1], lb, hb);
+        uint32_t la, lb;
+        split_f16e5x2(v[4 * j], v[4 * j + 1], main[2 * j], la);
+        split_f16e5x2(v[4 * j + 2], v[4 * j + 3], main[2 * j + 1], lb);
         lo4[j] = la | (lb << 16);
-        hi4[j] = ha | (hb << 16);
+        hi4[j] = f16e5_hi4(main[2 * j], main[2 * j + 1]);
     }
 }
 

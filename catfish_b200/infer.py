@@ -76,6 +76,32 @@ class IntervalList(collections.abc.Sequence):
         return (IntervalList, (np.ascontiguousarray(self.array),))
 
 
+_POOL = None
+
+
+def _concat_into(stage, arrays, offsets):
+    """Ragged concat of the batch into the pinned staging buffer.  Large batches are split into a few
+    contiguous groups copied by worker threads (numpy releases the GIL while copying): one thread moves
+    ~10 GB/s, which for a 128 MB batch is a tenth of the GPU time of the whole call."""
+    global _POOL
+    total = int(offsets[-1])
+    workers = min(8, os.cpu_count() or 1)
+    if total < (1 << 23) or len(arrays) < 2 * workers or workers < 2:
+        np.concatenate(arrays, out=stage)
+        return
+    if _POOL is None:
+        import concurrent.futures
+        _POOL = concurrent.futures.ThreadPoolExecutor(max_workers=workers, thread_name_prefix="catfish-stage")
+    cuts = np.searchsorted(offsets, np.linspace(0, total, workers + 1)[1:-1]).tolist()
+    bounds = [0] + cuts + [len(arrays)]
+    jobs = []
+    for lo, hi in zip(bounds, bounds[1:]):
+        if hi > lo:
+            jobs.append(_POOL.submit(np.concatenate, arrays[lo:hi], out=stage[int(offsets[lo]):int(offsets[hi])]))
+    for j in jobs:
+        j.result()
+
+
 def _staging(torch, device, n):
     """Pinned host buffer of at least n int16 samples for `device` (grows geometrically, reused across calls)."""
     buf = _STAGING.get(device)
@@ -140,22 +166,101 @@ def infer_reads(raws, model, threshold=0.5, min_run=15, extension_left=11, exten
     if n_reads:
         offsets[1:] = np.cumsum([a.size for a in arrays])
     total = int(offsets[-1])
+    lengths = [int(a.size) for a in arrays]
+    if total >= _PIPELINE_MIN_SAMPLES and not return_scores:
+        intervals, ioff = _infer_reads_pipelined(arrays, offsets, model, threshold, min_run, extension_left,
+                                                 extension_right)
+        bounds = ioff.tolist()
+        return [IntervalList(intervals[bounds[r]:bounds[r + 1]]) for r in range(n_reads)], lengths
     if n_reads:
         stage = _staging(_torch(), int(model.device), total).numpy()[:total]
-        np.concatenate(arrays, out=stage)
+        _concat_into(stage, arrays, offsets)
         raw = stage
     else:
         raw = np.zeros(0, np.int16)
     res = infer_concatenated(raw, offsets, model, threshold, min_run, extension_left, extension_right,
                              return_scores)
     intervals, ioff = res[0], res[1]
-    lengths = [int(a.size) for a in arrays]
     bounds = ioff.tolist()
     hps = [IntervalList(intervals[bounds[r]:bounds[r + 1]]) for r in range(n_reads)]
     if return_scores:
         scores = [res[2][int(offsets[r]):int(offsets[r + 1])] for r in range(n_reads)]
         return hps, lengths, scores
     return hps, lengths
+
+
+_PIPELINE_MIN_SAMPLES = 24_000_000      # batches of at least ~2 engine passes take the pipelined path
+_GROUP_SAMPLES = 10_400_000             # one engine pass (2368 tiles of 128 windows) per group
+_DEVBUF = {}                            # device index -> dict of cached device / pinned result buffers
+
+
+def _infer_reads_pipelined(arrays, offsets, model, threshold, min_run, ext_left, ext_right):
+    """A large ragged batch as a pipeline of groups of whole reads (about one engine pass each): while the GPU
+    works on group g (asynchronous ``cf_infer_reads`` on the device-resident copy), the host concatenates
+    group g+1 into pinned staging and starts its copy - the host pass over the signal disappears behind the
+    kernels instead of preceding them.  Same results as one ``cf_infer_reads_host`` call (reads are independent;
+    batch invariance is part of the parity suite).  Returns (intervals [n, 2], interval_offsets [R + 1])."""
+    torch = _torch()
+    lib = _cabi.load_library()
+    dev = int(model.device)
+    n_reads = len(arrays)
+    total = int(offsets[-1])
+    # groups of consecutive reads
+    cuts = [0]
+    while cuts[-1] < n_reads:
+        lo = cuts[-1]
+        hi = int(np.searchsorted(offsets, offsets[lo] + _GROUP_SAMPLES, side="right")) - 1
+        cuts.append(min(n_reads, max(hi, lo + 1)))
+    groups = list(zip(cuts[:-1], cuts[1:]))
+    caps = [int(lib.cf_max_intervals(int(offsets[hi] - offsets[lo]), hi - lo, min_run)) for lo, hi in groups]
+    cap_off = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream()
+        buf = _DEVBUF.setdefault(dev, {})
+        if buf.get("n_raw", 0) < total:
+            buf["raw"] = torch.empty(total + total // 4, dtype=torch.int16, device="cuda")
+            buf["n_raw"] = buf["raw"].numel()
+        if buf.get("n_iv", 0) < cap_off[-1]:
+            buf["iv"] = torch.empty((int(cap_off[-1]) * 5 // 4, 2), dtype=torch.int64, device="cuda")
+            buf["iv_pin"] = torch.empty((int(cap_off[-1]) * 5 // 4, 2), dtype=torch.int64).pin_memory()
+            buf["n_iv"] = buf["iv"].shape[0]
+        n_off = n_reads + len(groups)
+        if buf.get("n_off", 0) < n_off:
+            buf["ioff"] = torch.empty(n_off * 2, dtype=torch.int64, device="cuda")
+            buf["ioff_pin"] = torch.empty(n_off * 2, dtype=torch.int64).pin_memory()
+            buf["n_off"] = n_off * 2
+        stage_t = _staging(torch, dev, total)
+        stage = stage_t.numpy()
+        raw_dev, iv_dev, ioff_dev = buf["raw"], buf["iv"], buf["ioff"]
+        for g, (lo, hi) in enumerate(groups):
+            a, b = int(offsets[lo]), int(offsets[hi])
+            _concat_into(stage[a:b], arrays[lo:hi], offsets[lo:hi + 1] - offsets[lo])
+            raw_dev[a:b].copy_(stage_t[a:b], non_blocking=True)
+            off_g = np.ascontiguousarray(offsets[lo:hi + 1])
+            _cabi.check(lib.cf_infer_reads(
+                model.handle, raw_dev.data_ptr(), _offsets_ptr(off_g), hi - lo, None,
+                iv_dev.data_ptr() + 16 * int(cap_off[g]), ioff_dev.data_ptr() + 8 * (lo + g), caps[g],
+                float(threshold), int(min_run), int(ext_left), int(ext_right), stream.cuda_stream))
+        buf["ioff_pin"][:n_off].copy_(ioff_dev[:n_off], non_blocking=True)
+        stream.synchronize()
+        ioff_all = buf["ioff_pin"].numpy()
+        ioff = np.zeros(n_reads + 1, np.int64)
+        found = []
+        for g, (lo, hi) in enumerate(groups):
+            local = ioff_all[lo + g:hi + g + 1]
+            n_g = int(local[-1])
+            if n_g > caps[g]:
+                raise _cabi.CatfishError("interval capacity exceeded (%d > %d)" % (n_g, caps[g]))
+            ioff[lo + 1:hi + 1] = ioff[lo] + local[1:]
+            found.append(n_g)
+            if n_g:
+                c0 = int(cap_off[g])
+                buf["iv_pin"][c0:c0 + n_g].copy_(iv_dev[c0:c0 + n_g], non_blocking=True)
+        stream.synchronize()
+        iv_pin = buf["iv_pin"].numpy()
+        parts = [iv_pin[int(cap_off[g]):int(cap_off[g]) + n_g] for g, n_g in enumerate(found) if n_g]
+        intervals = np.concatenate(parts) if parts else np.zeros((0, 2), np.int64)
+    return intervals, ioff
 
 
 def infer_concatenated(raw, offsets, model, threshold=0.5, min_run=15, extension_left=11,

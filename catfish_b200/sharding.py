@@ -86,13 +86,13 @@ def gather_intervals(local_indices, local_hps, local_lengths, n_reads, rank, wor
     return hps, lengths
 
 
-def infer_reads_sharded(raws, model, rank, world_size, batch_reads=512, **kwargs):
+def infer_reads_sharded(raws, model, rank, world_size, batch_reads=512, lengths=None, **kwargs):
     """The reference's loop over all reads (catfish/catfish:55-56) sharded by read over ``world_size`` GPUs:
     this rank runs ``infer.infer_reads`` over its LPT shard in batches of ``batch_reads`` reads; (hps, lengths)
-    for ALL reads, in read order, on rank 0 (None elsewhere).  ``raws[i]`` is only touched for reads of this
-    rank's shard, so a caller may pass a lazy sequence."""
+    for ALL reads, in read order, on rank 0 (None elsewhere).  With ``lengths`` given, ``raws[i]`` is only touched
+    for reads of this rank's shard, so a caller may pass a lazy sequence that holds just those."""
     from . import infer
-    idx = shard_for_rank([len(r) for r in raws], rank, world_size)
+    idx = shard_for_rank(lengths if lengths is not None else [len(r) for r in raws], rank, world_size)
     hps, lengths = [], []
     for b in range(0, len(idx), batch_reads):
         h, l = infer.infer_reads([raws[int(i)] for i in idx[b:b + batch_reads]], model, **kwargs)

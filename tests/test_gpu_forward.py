@@ -280,6 +280,16 @@ def test_large_host_call_equals_smaller_calls():
         assert np.array_equal(ioff2, ioff[lo:hi + 1] - ioff[lo])
         assert np.array_equal(iv2, iv[ioff[lo]:ioff[hi]])
         assert np.array_equal(scores2, scores[off[lo]:off[hi]])
+    # the Python entry point takes the pipelined path for a batch of this size (groups of reads, device-side
+    # calls overlapped with the host's staging): identical per-read results, list-like and as arrays
+    assert int(off[-1]) >= infer._PIPELINE_MIN_SAMPLES
+    hps, lens = infer.infer_reads(reads, m)
+    assert lens == [len(r) for r in reads]
+    for r in range(len(reads)):
+        assert np.array_equal(hps[r].array, iv[ioff[r]:ioff[r + 1]])
+    assert hps[7] == iv[ioff[7]:ioff[8]].tolist() and isinstance(hps[7][0][0], int)
+    hps_again, _ = infer.infer_reads(reads, m)                     # cached staging / device buffers reused
+    assert all(a == b for a, b in zip(hps, hps_again))
 
 
 def test_fast5_entry_point_with_stub_h5py(tmp_path, monkeypatch, shipped_weights):

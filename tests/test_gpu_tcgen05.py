@@ -34,10 +34,14 @@ def _f16e5_emulated(a, w, s=64.0):
 
     def rnd(x, dt):
         return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dt).to(torch.float32).numpy().astype(np.float64)
-    ah, wh = rnd(a, torch.float16), rnd(w, torch.float16)
+    wh = rnd(w, torch.float16)
+    ah = s * rnd(rnd(a, torch.float16) / s, torch.float16)     # the main plane stores fp16(fp16(a) / S)
     al, wl = a.astype(np.float64) - ah, w.astype(np.float64) - wh
     e5 = torch.float8_e5m2
-    return ah @ wh + rnd(al * s, e5) @ rnd(wh / s, e5) + rnd(ah / s, e5) @ rnd(wl * s, e5)
+    # the a_h / S byte is the TOP BYTE of fp16(a_h / S): e5m2 of the same value truncated to two mantissa bits
+    top = (torch.from_numpy(np.ascontiguousarray(ah / s, np.float32)).to(torch.float16).view(torch.int16) & -256)
+    ah_s = top.view(torch.float16).to(torch.float32).numpy().astype(np.float64)
+    return ah @ wh + rnd(al * s, e5) @ rnd(wh / s, e5) + ah_s @ rnd(wl * s, e5)
 
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["ss", "ts"])

@@ -10,8 +10,9 @@ elementwise math stay exact, as in the CUDA engine.  Schemes:
   bf16x3     a_hi w_hi + a_lo w_hi + a_hi w_lo, bf16 pieces              (the shipped scheme, 3 passes)
   bf16x1     one bf16 pass                          fp16x1   one fp16 pass
   fp16x2     (a_hi + a_lo) w_hi, fp16 pieces                               (2 passes)
-  fp16+e5m2  a_hi w_hi in fp16 + [a_lo 2^s | a_hi 2^-s] [w_hi 2^-s ; w_lo 2^s] in e5m2
-             (1 fp16 pass + 1 fp8 pass with doubled K = 2 pass-equivalents; DESIGN.md section 5)
+  fp16+e5m2  a_hi w_hi in fp16 + [a_lo 2^s | a_hi 2^-s] [w_hi 2^-s ; w_lo 2^s] in e5m2, the a_hi 2^-s byte
+             truncated (it is the top byte of the fp16 value, never stored in HBM)
+             (1 fp16 pass + 1 fp8 pass with doubled K = 2 pass-equivalents; DESIGN.md section 4)
 Test infrastructure only (imports oracle/).
 """
 import os
@@ -27,6 +28,12 @@ from oracle import postprocess, tf_graph  # noqa: E402
 
 def rnd(x, dt):
     return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dt).to(torch.float32).numpy().astype(np.float64)
+
+
+def trunc_e5(x):
+    """Top byte of fp16(x): the e5m2 of x truncated toward zero to two mantissa bits."""
+    h = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.float16)
+    return (h.view(torch.int16) & -256).view(torch.float16).to(torch.float32).numpy().astype(np.float64)
 
 
 def make_mm(scheme, s_corr=6):
@@ -53,11 +60,12 @@ def make_mm(scheme, s_corr=6):
             ah, al = split(a, hf)
             return (ah + al) @ rnd(w, hf)
         if scheme == "fp16+e5m2":
-            ah = rnd(a, hf)
             wh = rnd(w, hf)
+            ah = 2.0 ** s_corr * rnd(rnd(a, hf) / 2.0 ** s_corr, hf)      # main plane = fp16(fp16(a) 2^-s)
             al, wl = a - ah, w - wh
             k = 2.0 ** s_corr
-            corr = rnd(al * k, e5) @ rnd(wh / k, e5) + rnd(ah / k, e5) @ rnd(wl * k, e5)
+            # the a_hi 2^-s byte is the top byte of the fp16 main value (truncated e5m2), as the kernels build it
+            corr = rnd(al * k, e5) @ rnd(wh / k, e5) + trunc_e5(ah / k) @ rnd(wl * k, e5)
             return ah @ wh + corr
         raise ValueError(scheme)
     return mm
