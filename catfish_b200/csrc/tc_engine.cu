@@ -1492,6 +1492,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
                     const uint32_t st = cn % Cfg::kStages;
                     mbar_wait(&bars[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
+                    if (lane == 0) CF_TR(c, gs, 60 + kk);
                     tc_fence_after_sync();
                     const uint32_t a0 = s0 + Cfg::kRing + st * 8192;
                     if (kE5) {

@@ -5,7 +5,7 @@
     python tools/timeline_report.py gpurun_out/trace.txt
 
 Regions 0/1 = MMA issuer of chain 0/1, 2/3 = epilogue of chain 0/1.  Tags (tc_engine.cu, CF_TR):
-issuer 10 x-part start, 20+kk chunk kk issued, 30 h ready, 31 gate MMAs issued, 40 r*h ready, 41 candidate
+issuer 10 x-part start, 60+kk chunk kk's data there, 20+kk chunk kk issued, 30 h ready, 31 gate MMAs issued, 40 r*h ready, 41 candidate
 MMAs issued; epilogue 50 gates landed, 51 r*h handed over, 52 update gate done, 53 candidate landed,
 54 accumulators drained, 55 new state handed over.
 """
