@@ -117,6 +117,7 @@ struct TcLayer {
     uint8_t* wfused = nullptr;        // [dir]{Wgx, Wcx, Wgh, Wch} as in GruFusedCfg (in = 32 or 128), exponent domain
     int fmt = 0;                      // operand format of wfused / of this layer's x and state operands
     float* bz = nullptr;              // [384] biases in the exponent domain
+    float* wxz = nullptr;             // [384] the single x row of gates / candidate kernels, exponent domain (in == 1)
 };
 
 struct TcEngine {
@@ -166,8 +167,8 @@ TcEngine* tc_create(const HostModel& hm) {
     {
         // fp16 + e5m2 operands need every tensor-core kernel of the pass to speak the format: the default
         // conv stack (two residual blocks) followed by fused GRU layers only
-        const bool covered = hm.desc.network_type == CF_NET_RESNET_RNN && hm.n_res() == 2 && hm.conv_channels() == kC &&
-                             e->use_fused;
+        const bool covered = e->use_fused && ((hm.desc.network_type == CF_NET_RESNET_RNN && hm.n_res() == 2 && hm.conv_channels() == kC) ||
+                                              hm.desc.network_type == CF_NET_RNN);
         const char* env = getenv("CF_TC_FMT");
         float wmax = 0.f;                             // the fp16 weight plane is stored times S = 64
         for (const GruDir& g : hm.gru) {
@@ -263,7 +264,7 @@ TcEngine* tc_create(const HostModel& hm) {
             pack_b_operand(g.wch.data(), kH, kH, kH, 0, &wh);
         }
         L.wh = tc_upload(e, wh);
-        if (L.in == kC || L.in == 2 * kH) {
+        if (L.in == kC || L.in == 2 * kH || L.in == 1) {
             auto build_fused = [&](int fmt) {
                 std::vector<__nv_bfloat16> wf;
                 for (int d = 0; d < 2; ++d) {
@@ -271,7 +272,7 @@ TcEngine* tc_create(const HostModel& hm) {
                     // exponent domain: gates scaled by -log2(e), candidate by 2 log2(e) (see sigmoid4_z / tanh4_z)
                     // x rows of gates/kernel and candidate/kernel side by side: one N = 192 operand
                     auto pack = fmt == kFmtF16E5 ? pack_b_operand_f16e5 : pack_b_operand;
-                    pack(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
+                    if (L.in > 1) pack(g.wx.data(), L.in, kNX, kNX, 0, &wf, kGateScale, 2 * kH, kCandScale);
                     pack(g.wgh.data(), kH, 2 * kH, 2 * kH, 0, &wf, kGateScale, 1 << 30, 1.f);
                     pack(g.wch.data(), kH, kH, kH, 0, &wf, kCandScale, 1 << 30, 1.f);
                 }
@@ -287,6 +288,15 @@ TcEngine* tc_create(const HostModel& hm) {
                 for (int j = 0; j < kNX; ++j)
                     bz[d * kNX + j] = hm.gru[2 * l + d].bx[j] * (j < 2 * kH ? kGateScale : kCandScale);
             L.bz = tc_upload(e, bz);
+            if (L.in == 1) {
+                // RNN-only layer 0 (neural_network.py:17-18): the x part of concat([x, h]) W is a rank-1 update
+                // x_t * w_row, added to the bias in the epilogue of the fused kernel - no MMA, no projection buffer
+                std::vector<float> wxz(2 * kNX);
+                for (int d = 0; d < 2; ++d)
+                    for (int j = 0; j < kNX; ++j)
+                        wxz[d * kNX + j] = hm.gru[2 * l + d].wx[j] * (j < 2 * kH ? kGateScale : kCandScale);
+                L.wxz = tc_upload(e, wxz);
+            }
         }
         e->layers.push_back(L);
     }
@@ -1308,15 +1318,16 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
 //   warp 19          : f16e5 input only - rebuilds each landed chunk's hi-byte slab from its main plane (the
 //                      compact HBM form carries 3 of the 4 operand bytes; tc_ptx.cuh) and hands the stage on
 template <int KX> struct GruF2Cfg {
+    static constexpr bool kNoX = KX == 1;                                 // scalar layer input: x part added in the epilogue
     static constexpr int kChunks = KX / 16;
     static constexpr int kStages = 10;                                    // ONE ring shared by both chains (see the producer)
     static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
-    static constexpr uint32_t kWgh = kWx + 2u * KX * kNX * 2;
+    static constexpr uint32_t kWgh = kWx + (kNoX ? 0u : 2u * KX * kNX * 2);
     static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;
     static constexpr uint32_t kWBytes = kWch + 2u * kH * 64 * 2;
     static constexpr uint32_t kRing = kWBytes;                            // [stage] x 8 KB
     static constexpr uint32_t kBias = kRing + (uint32_t)kStages * 8192;
-    static constexpr uint32_t kBars = kBias + 192 * 4;
+    static constexpr uint32_t kBars = kBias + 2 * 192 * 4;               // bias, then the scalar-input weight row
     static constexpr uint32_t kSmem = kBars + 512;
     // barriers: a chain's group of 8, then the ring's full / empty pairs, then the weight barrier
     static constexpr int kBarG = 0, kBarC = 1, kBarRh = 2, kBarH = 3, kBarCfree = 4, kBarXdone = 5;
@@ -1332,8 +1343,9 @@ __global__ void __launch_bounds__(kGruF2Threads, 1)
 tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ bias,
                      const __nv_bfloat16* __restrict__ x_blocks, __nv_bfloat16* __restrict__ y_out,
                      const float* __restrict__ head_w, float* __restrict__ head_part, int n_tiles,
-                     long long* __restrict__ trace) {
+                     long long* __restrict__ trace, const float* __restrict__ x_scalar, const float* __restrict__ wx_scalar) {
     using Cfg = GruF2Cfg<KX>;
+    constexpr bool kNoX = Cfg::kNoX;
     // debug timeline (CF_TC_TRACE): block 0 records (tag, SM clock) pairs for steps 36..39 of each role
     int tr_n = 0;
 #define CF_TR(region, step, tag)                                                                   \
@@ -1386,8 +1398,10 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #ifndef CF_PRECISE_ACT
     // bias pre-multiplied by the activation's argument scale, so that bias add + scaling is one FFMA
     if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x] * (threadIdx.x < 2 * kH ? kSigArgScale : kTanhArgScale);
+    if (kNoX && threadIdx.x < 192) bias_s[192 + threadIdx.x] = wx_scalar[dir * kNX + threadIdx.x] * (threadIdx.x < 2 * kH ? kSigArgScale : kTanhArgScale);
 #else
     if (threadIdx.x < 192) bias_s[threadIdx.x] = bias[dir * kNX + threadIdx.x];
+    if (kNoX && threadIdx.x < 192) bias_s[192 + threadIdx.x] = wx_scalar[dir * kNX + threadIdx.x];
 #endif
     if (warp == 16) tmem_alloc<512>(tmem_slot);
     tc_fence_before_sync();
@@ -1412,7 +1426,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             const uint8_t* xbase = reinterpret_cast<const uint8_t*>(x_blocks);
             const int total0 = tiles_of(0) * kWindow, total1 = tiles_of(1) * kWindow;     // total1 <= total0
             uint32_t st = 0, par = 1;                     // ring position; parity of the empty barrier's previous phase
-            for (int gs = 0; gs < total0; ++gs) {
+            for (int gs = 0; gs < (kNoX ? 0 : total0); ++gs) {
                 for (int c = 0; c < 2; ++c) {
                     if (c == 1 && gs >= total1) break;
                     const uint8_t* xb = xbase + blk_of(c, gs) * blk_bytes;
@@ -1484,7 +1498,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 // An mbarrier wait only tells phases apart by parity, so a consumer must never look at a stage two
                 // uses ahead of it: the issuers take their ring entries strictly in turn - this one starts after the
                 // other chain's issuer has passed the full-waits of the entry before.
-                if (c == 1) mbar_wait(&bars[Cfg::kBarXdone], gs & 1);
+                if (kNoX) {
+                } else if (c == 1) mbar_wait(&bars[Cfg::kBarXdone], gs & 1);
                 else if (gs > 0 && gs - 1 < total1) mbar_wait(&bars[8 + Cfg::kBarXdone], (gs - 1) & 1);
                 // x part: needs the previous step's accumulators drained
                 if (gs > 0) mbar_wait(&b[Cfg::kBarCfree], (gs - 1) & 1);
@@ -1512,7 +1527,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     umma_commit_pred(&bars[Cfg::kBarEmpty + st], elected);
                     if (lane == 0) CF_TR(c, gs, 20 + kk);
                 }
-                if (lane == 0) mbar_arrive(&b[Cfg::kBarXdone]);
+                if (!kNoX && lane == 0) mbar_arrive(&b[Cfg::kBarXdone]);
                 // state part of the gates
                 mbar_wait(&b[Cfg::kBarH], par);
                 if (lane == 0) CF_TR(c, gs, 30);
@@ -1521,7 +1536,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #pragma unroll
                     for (int kk = 0; kk < kH / 16; ++kk) {
                         const uint32_t wp = s0 + Cfg::kWgh + kk * 2 * (128 * 16);
-                        umma_bf16_ts_pred(dg, ta + kk * 8, make_smem_desc(wp, 128 * 16, 128), idesc_g, 1, elected);
+                        umma_bf16_ts_pred(dg, ta + kk * 8, make_smem_desc(wp, 128 * 16, 128), idesc_g, !kNoX || kk != 0, elected);
                         if (!(kExp & 2))
                         umma_f8_ts_pred(dg, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 128 * 2, 128 * 16, 128), idesc_g8, 1, elected);
                     }
@@ -1532,7 +1547,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                         const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
 #pragma unroll
                         for (int kk = 0; kk < kH / 16; ++kk)
-                            umma_bf16_ts_pred(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g, 1, elected);
+                            umma_bf16_ts_pred(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g,
+                                              !kNoX || (pass | kk) != 0, elected);
                     }
                 }
                 umma_commit_pred(&b[Cfg::kBarG], elected);
@@ -1545,7 +1561,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #pragma unroll
                     for (int kk = 0; kk < kH / 16; ++kk) {
                         const uint32_t wp = s0 + Cfg::kWch + kk * 2 * (64 * 16);
-                        umma_bf16_ts_pred(dc, ta + kk * 8, make_smem_desc(wp, 64 * 16, 128), idesc_c, 1, elected);
+                        umma_bf16_ts_pred(dc, ta + kk * 8, make_smem_desc(wp, 64 * 16, 128), idesc_c, !kNoX || kk != 0, elected);
                         if (!(kExp & 2))
                         umma_f8_ts_pred(dc, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 64 * 2, 64 * 16, 128), idesc_c8, 1, elected);
                     }
@@ -1556,7 +1572,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                         const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
 #pragma unroll
                         for (int kk = 0; kk < kH / 16; ++kk)
-                            umma_bf16_ts_pred(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c, 1, elected);
+                            umma_bf16_ts_pred(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c,
+                                              !kNoX || (pass | kk) != 0, elected);
                     }
                 }
                 umma_commit_pred(&b[Cfg::kBarC], elected);
@@ -1603,6 +1620,16 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             for (int s = 0; s < kWindow; ++s, ++gs) {
                 const uint32_t par = gs & 1;
                 const size_t blk = blk_of(chain, gs);
+                // scalar layer input (RNN-only layer 0): activation argument = acc + (b + x_t w), one extra FMA per value
+                const float xv = kNoX ? __ldg(x_scalar + blk * 128 + row) : 0.f;
+                auto bias4 = [&](int idx) -> float4 {
+                    float4 b4 = *reinterpret_cast<const float4*>(bias_s + idx);
+                    if (kNoX) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(bias_s + 192 + idx);
+                        b4.x = fmaf(xv, w4.x, b4.x); b4.y = fmaf(xv, w4.y, b4.y); b4.z = fmaf(xv, w4.z, b4.z); b4.w = fmaf(xv, w4.w, b4.w);
+                    }
+                    return b4;
+                };
                 // ---- reset gate -> r*h operand
                 mbar_wait(&b[Cfg::kBarG], par);
                 if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 50);
@@ -1617,7 +1644,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + c0 + i);
+                            const float4 b4 = bias4(j0 + c0 + i);
 #ifndef CF_PRECISE_ACT
                             const float2 r0 = sigmoid_zb2(make_float2(__uint_as_float(ar[c0 + i]), __uint_as_float(ar[c0 + i + 1])), make_float2(b4.x, b4.y));
                             const float2 r1 = sigmoid_zb2(make_float2(__uint_as_float(ar[c0 + i + 2]), __uint_as_float(ar[c0 + i + 3])), make_float2(b4.z, b4.w));
@@ -1649,7 +1676,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + kH + j0 + i);
+                        const float4 b4 = bias4(kH + j0 + i);
 #ifndef CF_PRECISE_ACT
                         u2[i >> 1] = sigmoid_zb2(make_float2(__uint_as_float(au[i]), __uint_as_float(au[i + 1])), make_float2(b4.x, b4.y));
                         u2[(i >> 1) + 1] = sigmoid_zb2(make_float2(__uint_as_float(au[i + 2]), __uint_as_float(au[i + 3])), make_float2(b4.z, b4.w));
@@ -1677,7 +1704,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 2 * kH + j0 + i);
+                    const float4 b4 = bias4(2 * kH + j0 + i);
 #ifndef CF_PRECISE_ACT
                     {
                         // h = c + u (h - c), two units per instruction
@@ -1803,39 +1830,51 @@ tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const 
 
 // ResNet-only head (resnet_class.py:23 commented out): dense 32 -> 1 + sigmoid straight from the
 // conv stack's output blocks ({hi, lo} x [4][128][8] bf16 per block), scattered to sample order.
-__global__ void tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ w, float b,
-                                    const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
-                                    const int32_t* __restrict__ read, const double* __restrict__ stats,
-                                    int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (tile, w, t) with t fastest
-    if (i >= n_rows) return;
-    const int t = (int)(i % kWindow);
-    const int64_t wi = i / kWindow;
-    const int wr = (int)(wi % kTileWindows);
-    const int64_t tile = wi / kTileWindows;
-    const int64_t g = (tile0 + tile) * kTileWindows + wr;
-    if (t >= valid[g]) return;
-    const __nv_bfloat16* blk = y + ((size_t)tile * kWindow + t) * (2 * 128 * kC);
-    float acc = b;
+// One CTA per tile, like tc_head_kernel: the operand blocks are read window-fastest (each warp reads 512
+// contiguous bytes per plane and K group), the logits are transposed through shared memory and the
+// probabilities written position-fastest (contiguous in the read).
+__global__ void __launch_bounds__(256)
+tc_head_conv_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ w, float b,
+                    const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
+                    const int32_t* __restrict__ read, const double* __restrict__ stats,
+                    int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits) {
+    __shared__ float logit[kWindow][kTileWindows + 1];
+    __shared__ float ws[kC];
+    const int64_t tile = blockIdx.x;
+    if (tile * kTileWindows * kWindow >= n_rows) return;
+    if (threadIdx.x < kC) ws[threadIdx.x] = w[threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWindow * kTileWindows; i += blockDim.x) {
+        const int t = i / kTileWindows, wr = i % kTileWindows;
+        const __nv_bfloat16* blk = y + ((size_t)tile * kWindow + t) * (2 * 128 * kC);
+        float acc = b;
 #pragma unroll
-    for (int kg = 0; kg < kC / 8; ++kg) {
-        const uint4 hi = *reinterpret_cast<const uint4*>(blk + ((size_t)kg * 128 + wr) * 8);
-        const uint4 lo = *reinterpret_cast<const uint4*>(blk + 128 * kC + ((size_t)kg * 128 + wr) * 8);
-        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+        for (int kg = 0; kg < kC / 8; ++kg) {
+            const uint4 hi = *reinterpret_cast<const uint4*>(blk + ((size_t)kg * 128 + wr) * 8);
+            const uint4 lo = *reinterpret_cast<const uint4*>(blk + 128 * kC + ((size_t)kg * 128 + wr) * 8);
+            const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float v0 = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
-            const float v1 = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
-            acc = fmaf(v0, __ldg(w + kg * 8 + 2 * k), acc);
-            acc = fmaf(v1, __ldg(w + kg * 8 + 2 * k + 1), acc);
+            for (int k = 0; k < 4; ++k) {
+                const float v0 = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+                const float v1 = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+                acc = fmaf(v0, ws[kg * 8 + 2 * k], acc);
+                acc = fmaf(v1, ws[kg * 8 + 2 * k + 1], acc);
+            }
         }
+        logit[t][wr] = acc;
     }
-    float p = want_logits ? acc : 1.f / (1.f + expf(-acc));
-    if (stats) {
-        const double sc = stats[2 * read[g] + 1];
-        if (!(sc > 0.0)) p = nanf("");
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWindow * kTileWindows; i += blockDim.x) {
+        const int wr = i / kWindow, t = i % kWindow;
+        const int64_t g = (tile0 + tile) * kTileWindows + wr;
+        if (t >= valid[g]) continue;
+        float p = want_logits ? logit[t][wr] : 1.f / (1.f + expf(-logit[t][wr]));
+        if (stats) {
+            const double sc = stats[2 * read[g] + 1];
+            if (!(sc > 0.0)) p = nanf("");
+        }
+        probs[src[g] + t] = p;
     }
-    probs[src[g] + t] = p;
 }
 
 // ====================================================================== forward
@@ -1868,6 +1907,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<128>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<1>::kSmem));
+        CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<1>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<32, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_gru_fused2_kernel<128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GruF2Cfg<128>::kSmem));
@@ -1920,7 +1961,7 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             __nv_bfloat16* yo = last ? nullptr : ybuf[l & 1];
             if (L.wfused && e->use_fused) {
                 // input projection + recurrence in one kernel; a_in is the A-operand form of the layer input
-                if (l == 0 && !a_in) {
+                if (l == 0 && !a_in && L.in == kC) {
                     ProfScope ps(prof, KC_K3_XPROJ, stream);
                     const int64_t total = rows * (kC / 8);
                     tc_pack_a_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(feat, kC, rows, a0);
@@ -1938,19 +1979,27 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 float* hp_l = last ? head_part : nullptr;
                 // operand format of this layer and of the layer that reads its output
                 const int fmt_out = last ? L.fmt : e->layers[l + 1].fmt;
-                if (L.in == kC) {
+                if (L.in == 1) {
+                    // scalar input (RNN-only layer 0): x part in the epilogue from the fp32 signal rows
+                    if (L.fmt == kFmtF16E5)
+                        tc_gru_fused2_kernel<1, 1, 1><<<grid2, kGruF2Threads, GruF2Cfg<1>::kSmem, stream>>>(
+                            L.wfused, L.bz, nullptr, yo, hw_l, hp_l, (int)tiles, nullptr, feat, L.wxz);
+                    else
+                        tc_gru_fused2_kernel<1, 0, 0><<<grid2, kGruF2Threads, GruF2Cfg<1>::kSmem, stream>>>(
+                            L.wfused, L.bz, nullptr, yo, hw_l, hp_l, (int)tiles, nullptr, feat, L.wxz);
+                } else if (L.in == kC) {
                     if (fmt_out == kFmtF16E5)
                         tc_gru_fused2_kernel<32, 0, 1><<<grid2, kGruF2Threads, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr);
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr, nullptr, nullptr);
                     else
                         tc_gru_fused2_kernel<32, 0, 0><<<grid2, kGruF2Threads, GruF2Cfg<32>::kSmem, stream>>>(
-                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr);
+                            L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, nullptr, nullptr, nullptr);
                 } else if (L.fmt == kFmtF16E5) {
                     tc_gru_fused2_kernel<128, 1, 1><<<grid2, kGruF2Threads, GruF2Cfg<128>::kSmem, stream>>>(
-                        L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev);
+                        L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev, nullptr, nullptr);
                 } else {
                     tc_gru_fused2_kernel<128, 0, 0><<<grid2, kGruF2Threads, GruF2Cfg<128>::kSmem, stream>>>(
-                        L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev);
+                        L.wfused, L.bz, a_in, yo, hw_l, hp_l, (int)tiles, trace_dev, nullptr, nullptr);
                 }
                 CF_LAUNCHED();
                 if (trace_dev) {
@@ -2007,7 +2056,7 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         if (n_layers == 0) {
             // ResNet-only: dense on the conv output
             ProfScope ps(prof, KC_K5_HEAD, stream);
-            tc_head_conv_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(
+            tc_head_conv_kernel<<<(unsigned)tiles, 256, 0, stream>>>(
                 a_in, e->head_w, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs, want_logits ? 1 : 0);
             CF_LAUNCHED();
         } else {
