@@ -53,7 +53,8 @@ if ROOT not in sys.path:
 METRIC = "raw_signal_samples_per_sec_resnetrnn_infer"
 UNIT = "samples/s"
 LEN_LO, LEN_HI = 50_000, 200_000
-JOB_READS = 4096
+JOB_READS = 16384
+JOB_POOL = 4096
 JOB_SEED = 20_000
 
 # algorithmic work per real sample (SURVEY.md section 8d / BASELINE.md section 4)
@@ -520,29 +521,40 @@ def job_leg(args, model, rank, world, barrier, max_over_ranks):
     import torch
     from catfish_b200 import infer, sharding, synth
     n = args.job_reads
-    lengths = synth.ragged_lengths(n, LEN_LO, LEN_HI, seed=JOB_SEED)
+    # read i is entry i % JOB_POOL of a pool of distinct seeded reads (generating 1e10 distinct synthetic samples
+    # on the host would take minutes); lengths and contents repeat with period JOB_POOL, results are per read
+    pool_len = synth.ragged_lengths(min(n, JOB_POOL), LEN_LO, LEN_HI, seed=JOB_SEED)
+    lengths = pool_len[np.arange(n) % len(pool_len)]
     mine = sharding.shard_for_rank(lengths, rank, world)
-    local = {int(i): synth.synth_read(int(lengths[i]), JOB_SEED * 7 + int(i)) for i in mine}     # only this rank's reads
+    local = {}
+    for i in mine:
+        k = int(i) % len(pool_len)
+        if k not in local:
+            local[k] = synth.synth_read(int(pool_len[k]), JOB_SEED * 7 + k)       # only what this rank's shard needs
 
     class Reads(object):
         def __len__(self):
             return n
 
         def __getitem__(self, i):
-            return local[int(i)]
+            return local[int(i) % len(pool_len)]
 
     reads = Reads()
-    infer.infer_reads([local[int(i)] for i in mine[:args.reads_per_step]], model)      # warm-up: staging buffers, workspace
+    # warm-up: staging buffers, workspace, and the communicator paths the gather uses (first NCCL all_gather /
+    # gather calls set up their channels, which takes longer than the whole job)
+    wh, wl = infer.infer_reads([reads[int(i)] for i in mine[:args.reads_per_step]], model)
+    sharding.gather_intervals(mine[:len(wh)], wh, wl, n, rank, world)
     barrier()
     t0 = time.perf_counter()
-    res = sharding.infer_reads_sharded(reads, model, rank, world, lengths=lengths, batch_reads=args.reads_per_step)
+    res = sharding.infer_reads_sharded(reads, model, rank, world, batch_reads=args.reads_per_step, lengths=lengths)
     torch.cuda.synchronize()
     secs = max_over_ranks(time.perf_counter() - t0)
     loads = [int(lengths[p].sum()) for p in sharding.partition_reads(lengths, world)]
     out = {"reads": n, "samples": int(lengths.sum()), "seconds": secs, "reads_per_sec": n / secs,
            "samples_per_sec": float(lengths.sum()) / secs, "scaling": "strong", "n_gpus": world,
            "rank_load_max_over_min": max(loads) / max(1, min(loads)),
-           "note": "LPT shards by read, infer.infer_reads per batch of %d reads, gather_intervals on rank 0, all "
+           "distinct_reads": int(min(n, JOB_POOL)),
+           "note": "LPT shards by read, infer.infer_reads_arrays per batch of %d reads, gather_csr on rank 0, all "
                    "inside the timed region (host wall clock, max over ranks); result_sha1 is over the merged "
                    "per-read (length, intervals) in read order and must not depend on n_gpus" % args.reads_per_step}
     if rank == 0:

@@ -155,6 +155,20 @@ def infer_reads(raws, model, threshold=0.5, min_run=15, extension_left=11, exten
     normalisation, windowing, network, threshold / short-run removal / interval emission,
     device->host copy of the results.  The ragged batch is concatenated straight into a pinned staging
     buffer (one host pass, then DMA at PCIe rate instead of a pageable copy)."""
+    res = infer_reads_arrays(raws, model, threshold, min_run, extension_left, extension_right, window_size,
+                             return_scores)
+    intervals, ioff, lengths = res[0], res[1], res[2]
+    bounds = ioff.tolist()
+    hps = [IntervalList(intervals[bounds[r]:bounds[r + 1]]) for r in range(len(lengths))]
+    if return_scores:
+        return hps, lengths.tolist(), res[3]
+    return hps, lengths.tolist()
+
+
+def infer_reads_arrays(raws, model, threshold=0.5, min_run=15, extension_left=11, extension_right=16,
+                       window_size=35, return_scores=False):
+    """``infer_reads`` with the result left in CSR form: ``(intervals int64 [n, 2], interval_offsets int64 [R + 1],
+    lengths int64 [R][, scores list])`` - what the sharded job gathers (no per-read Python objects)."""
     if window_size != model.window:
         raise ValueError("window_size must equal the model's window (%d)" % model.window)
     arrays = [_as_int16(r) for r in raws]
@@ -162,16 +176,14 @@ def infer_reads(raws, model, threshold=0.5, min_run=15, extension_left=11, exten
         if a.size == 0:
             raise IndexError("list index out of range")        # infer.py:184 on an empty read
     n_reads = len(arrays)
+    lengths = np.array([a.size for a in arrays], np.int64)
     offsets = np.zeros(n_reads + 1, np.int64)
-    if n_reads:
-        offsets[1:] = np.cumsum([a.size for a in arrays])
+    np.cumsum(lengths, out=offsets[1:])
     total = int(offsets[-1])
-    lengths = [int(a.size) for a in arrays]
     if total >= _PIPELINE_MIN_SAMPLES and not return_scores:
         intervals, ioff = _infer_reads_pipelined(arrays, offsets, model, threshold, min_run, extension_left,
                                                  extension_right)
-        bounds = ioff.tolist()
-        return [IntervalList(intervals[bounds[r]:bounds[r + 1]]) for r in range(n_reads)], lengths
+        return intervals, ioff, lengths
     if n_reads:
         stage = _staging(_torch(), int(model.device), total).numpy()[:total]
         _concat_into(stage, arrays, offsets)
@@ -180,13 +192,10 @@ def infer_reads(raws, model, threshold=0.5, min_run=15, extension_left=11, exten
         raw = np.zeros(0, np.int16)
     res = infer_concatenated(raw, offsets, model, threshold, min_run, extension_left, extension_right,
                              return_scores)
-    intervals, ioff = res[0], res[1]
-    bounds = ioff.tolist()
-    hps = [IntervalList(intervals[bounds[r]:bounds[r + 1]]) for r in range(n_reads)]
     if return_scores:
         scores = [res[2][int(offsets[r]):int(offsets[r + 1])] for r in range(n_reads)]
-        return hps, lengths, scores
-    return hps, lengths
+        return res[0], res[1], lengths, scores
+    return res[0], res[1], lengths
 
 
 _PIPELINE_MIN_SAMPLES = 24_000_000      # batches of at least ~2 engine passes take the pipelined path
