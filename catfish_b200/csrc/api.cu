@@ -305,9 +305,9 @@ static int handle_end(cf_model* m, cudaStream_t st);
 
 static int engine_forward(cf_model* m, const int16_t* raw, const double* stats, const float* xwin,
                           WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream,
-                          bool want_logits = false) {
+                          bool want_logits = false, const LabelBits* bits = nullptr) {
     if (m->engine == CF_ENGINE_TCGEN05)
-        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits);
+        return tc_forward(m->tc, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits, bits);
     return simt_forward(m->simt, m->hm, raw, stats, xwin, tab, n_tiles, probs, stream, &m->prof, want_logits);
 }
 
@@ -454,8 +454,15 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
     CF_TRY(m->stats.ensure(sizeof(double) * 2 * (size_t)n_reads));
     WindowTable tab;
     CF_TRY(ensure_table(m, plan.n_tiles, &tab));
+    // When the caller does not want the probabilities, the head kernel thresholds them itself and emits label bits
+    // (no 4 B/sample write + 4 B/sample read between the network and the interval caller).
+    const bool fused_bits = !probs_dev && m->engine == CF_ENGINE_TCGEN05 && tc_can_emit_bits(m->tc);
+    LabelBits bits;
+    bits.threshold = threshold;
     float* probs = probs_dev;
-    if (!probs) {
+    if (fused_bits) {
+        CF_TRY(k6_bits_prepare(m->k6, plan.total_samples, &bits, stream));
+    } else if (!probs) {
         CF_TRY(m->probs_internal.ensure(sizeof(float) * (size_t)plan.total_samples));
         probs = m->probs_internal.as<float>();
     }
@@ -470,10 +477,16 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
     }
     {
         ProfScope ps(&m->prof, KC_K1_TABLE, stream);
-        CF_TRY(k1_window_table(offsets_dev, win_off_dev, n_reads, plan.total_windows, plan.n_tiles, tab, stream));
+        CF_TRY(k1_window_table(offsets_dev, win_off_dev, n_reads, plan.total_windows, plan.n_tiles, tab, stream,
+                               fused_bits ? bits.bwords : nullptr, plan.total_samples));
     }
-    CF_TRY(engine_forward(m, raw0, m->stats.as<double>(), nullptr, tab, plan.n_tiles, probs, stream));
-    {
+    CF_TRY(engine_forward(m, raw0, m->stats.as<double>(), nullptr, tab, plan.n_tiles, probs, stream, false,
+                          fused_bits ? &bits : nullptr));
+    if (fused_bits) {
+        ProfScope ps(&m->prof, KC_K6_INTERVALS, stream, 3);
+        CF_TRY(k6_intervals_from_bits(m->k6, bits, offsets_dev, n_reads, plan.total_samples, intervals_dev,
+                                      interval_offsets_dev, capacity, min_run, ext_left, ext_right, stream));
+    } else {
         ProfScope ps(&m->prof, KC_K6_INTERVALS, stream, 7);
         CF_TRY(k6_call_intervals(m->k6, probs, BITS_FROM_F32, threshold, 1, offsets_dev, n_reads,
                                  plan.total_samples, intervals_dev, interval_offsets_dev, nullptr, capacity,

@@ -347,8 +347,12 @@ int k1_normalize_f64(const int16_t* raw, const int64_t* offsets_dev, int32_t n_r
 __global__ void k1_window_table_kernel(const int64_t* __restrict__ offsets, const int64_t* __restrict__ win_off,
                                        int n_reads, int64_t total_windows, int64_t n_slots,
                                        int64_t* __restrict__ src, int32_t* __restrict__ valid,
-                                       int32_t* __restrict__ read) {
+                                       int32_t* __restrict__ read, unsigned* __restrict__ bwords, int64_t total_samples) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bwords && g < n_reads) {             // read-start bits for the interval caller (k6): one per non-empty read
+        const int64_t o = offsets[g];
+        if (o < total_samples && offsets[g + 1] > o) atomicOr(&bwords[o >> 5], 1u << (o & 31));
+    }
     if (g >= n_slots) return;
     if (g >= total_windows) { src[g] = -1; valid[g] = 0; read[g] = -1; return; }
     const int r = find_segment(win_off, n_reads, g);
@@ -361,11 +365,13 @@ __global__ void k1_window_table_kernel(const int64_t* __restrict__ offsets, cons
 }
 
 int k1_window_table(const int64_t* offsets_dev, const int64_t* win_off_dev, int32_t n_reads,
-                    int64_t total_windows, int64_t n_tiles, WindowTable tab, cudaStream_t stream) {
+                    int64_t total_windows, int64_t n_tiles, WindowTable tab, cudaStream_t stream,
+                    unsigned* bwords, int64_t total_samples) {
     const int64_t slots = n_tiles * kTileWindows;
     if (slots <= 0) return CF_OK;
+    // every read has at least one window, so slots >= n_reads and thread g < n_reads exists for every read
     k1_window_table_kernel<<<(unsigned)ceil_div(slots, 256), 256, 0, stream>>>(
-        offsets_dev, win_off_dev, n_reads, total_windows, slots, tab.src, tab.valid, tab.read);
+        offsets_dev, win_off_dev, n_reads, total_windows, slots, tab.src, tab.valid, tab.read, bwords, total_samples);
     CF_LAUNCHED();
     return CF_OK;
 }

@@ -341,6 +341,164 @@ int k6_call_intervals(IntervalScratch& s, const void* values, int source, double
     return CF_OK;
 }
 
+// ---------------------------------------------------------------- label bits produced by the network's head kernel
+// S words are not stored: S[w] = L[w] & (~(L[w] << 1 | L[w-1] >> 31) | B[w]).
+__device__ __forceinline__ unsigned start_word(const unsigned* __restrict__ lwords, const unsigned* __restrict__ bwords, int64_t w) {
+    const unsigned L = lwords[w];
+    const unsigned carry = w > 0 ? lwords[w - 1] >> 31 : 0u;
+    return L & (~((L << 1) | carry) | bwords[w]);
+}
+__device__ __forceinline__ int64_t run_start_lb(const unsigned* __restrict__ lwords, const unsigned* __restrict__ bwords, int64_t w, int eb) {
+    unsigned s = start_word(lwords, bwords, w) & (eb == 31 ? 0xffffffffu : ((2u << eb) - 1u));
+    while (s == 0) {
+        --w;
+        s = start_word(lwords, bwords, w);
+    }
+    return (w << 5) + (31 - __clz(s));
+}
+
+// Count (EMIT = false): qualifying run ends per block; the LAST block to finish scans the block counts into
+// block_base (so no separate scan launch).  Emit (EMIT = true): intervals in global rank order.
+template <bool EMIT>
+__global__ void __launch_bounds__(kWordsPerBlock)
+k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restrict__ bwords, int64_t n_words,
+                    const int64_t* __restrict__ offsets, int n_reads, int min_run, int ext_left, int ext_right,
+                    unsigned* __restrict__ block_cnt, int64_t* __restrict__ block_base, unsigned* __restrict__ done_counter,
+                    int64_t* __restrict__ run_start_global, int64_t* __restrict__ intervals, int64_t capacity) {
+    __shared__ unsigned warp_sums[kWordsPerBlock / 32];
+    __shared__ long long scan_sums[kWordsPerBlock / 32];
+    __shared__ long long scan_carry;
+    __shared__ int is_last;
+    const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
+    unsigned L = 0, E = 0;
+    if (w < n_words) {
+        L = lwords[w];
+        unsigned next = 0, bnext = 0;
+        if (w + 1 < n_words) { next = lwords[w + 1] & 1u; bnext = bwords[w + 1] & 1u; }
+        E = L & (~((L >> 1) | (next << 31)) | (bwords[w] >> 1) | (bnext << 31));
+    }
+    unsigned qual = 0;
+    int64_t starts[4];
+    int nq = 0;
+    for (unsigned e = E; e; e &= e - 1) {
+        const int eb = __ffs(e) - 1;
+        const int64_t s = run_start_lb(lwords, bwords, w, eb);
+        const int64_t len = (w << 5) + eb - s + 1;
+        if (len >= min_run) {
+            qual |= 1u << eb;
+            if (nq < 4) starts[nq] = s;
+            ++nq;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = (unsigned)nq;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    unsigned base = 0, total = 0;
+    for (int i = 0; i < kWordsPerBlock / 32; ++i) {
+        unsigned v = warp_sums[i];
+        if (i < warp) base += v;
+        total += v;
+    }
+    if (!EMIT) {
+        if (threadIdx.x == 0) {
+            block_cnt[blockIdx.x] = total;
+            __threadfence();
+            is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+            scan_carry = 0;
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        const int64_t n = gridDim.x;
+        for (int64_t b0 = 0; b0 < n; b0 += kWordsPerBlock) {
+            const int64_t i = b0 + threadIdx.x;
+            const long long v = i < n ? (long long)__ldcg(block_cnt + i) : 0;
+            long long sc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                long long o = __shfl_up_sync(0xffffffffu, sc, d);
+                if (lane >= d) sc += o;
+            }
+            if (lane == 31) scan_sums[warp] = sc;
+            __syncthreads();
+            long long wbase = 0, tot = 0;
+            for (int k = 0; k < kWordsPerBlock / 32; ++k) {
+                const long long t = scan_sums[k];
+                if (k < warp) wbase += t;
+                tot += t;
+            }
+            const long long c = scan_carry;
+            if (i < n) block_base[i] = c + wbase + sc - v;
+            __syncthreads();
+            if (threadIdx.x == 0) scan_carry = c + tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { block_base[n] = scan_carry; *done_counter = 0; }      // counter reset for the next call
+    } else {
+        int64_t rank = block_base[blockIdx.x] + base + inc - (unsigned)nq;
+        int k = 0;
+        for (unsigned q = qual; q; q &= q - 1, ++k, ++rank) {
+            const int eb = __ffs(q) - 1;
+            const int64_t s = k < 4 ? starts[k] : run_start_lb(lwords, bwords, w, eb);
+            const int64_t len = (w << 5) + eb - s + 1;
+            run_start_global[rank] = s;
+            if (rank < capacity) {
+                const int64_t local = s - offsets[find_read(offsets, n_reads, s)];
+                intervals[2 * rank] = local - ext_left;
+                intervals[2 * rank + 1] = local + len + ext_right;
+            }
+        }
+    }
+}
+
+int k6_bits_prepare(IntervalScratch& s, int64_t total_samples, LabelBits* out, cudaStream_t stream) {
+    const int64_t n_words = ceil_div(total_samples > 0 ? total_samples : 1, 32);
+    CF_TRY(s.bits.ensure(sizeof(unsigned) * (size_t)(3 * (n_words + 1))));
+    CF_TRY(s.misc.ensure(256));
+    static_assert(sizeof(unsigned) == 4, "");
+    out->lwords = s.bits.as<unsigned>();
+    out->bwords = out->lwords + (n_words + 1);
+    CF_CUDA(cudaMemsetAsync(out->lwords, 0, sizeof(unsigned) * (size_t)(2 * (n_words + 1)), stream));
+    return CF_OK;
+}
+
+int k6_intervals_from_bits(IntervalScratch& s, const LabelBits& bits, const int64_t* offsets_dev, int32_t n_reads,
+                           int64_t total_samples, int64_t* intervals, int64_t* interval_offsets, int64_t capacity,
+                           int32_t min_run, int32_t ext_left, int32_t ext_right, cudaStream_t stream) {
+    const int64_t n = total_samples;
+    const int64_t n_words = ceil_div(n, 32);
+    const int64_t n_blocks = ceil_div(n_words, kWordsPerBlock);
+    CF_TRY(s.block_cnt.ensure(sizeof(unsigned) * (size_t)n_blocks + sizeof(int64_t) * (size_t)(n_blocks + 1) + 16));
+    int64_t* block_base = s.block_cnt.as<int64_t>();
+    unsigned* block_cnt = reinterpret_cast<unsigned*>(block_base + n_blocks + 1);
+    const int64_t max_runs = n / ((min_run < 1 ? 1 : min_run) + 1) + n_reads + 1;
+    CF_TRY(s.read_cnt.ensure(sizeof(int64_t) * (size_t)max_runs));
+    int64_t* run_start_global = s.read_cnt.as<int64_t>();
+    if (!s.misc_zeroed) {                       // the done counter resets itself after every use
+        CF_CUDA(cudaMemsetAsync(s.misc.ptr, 0, 256, stream));
+        s.misc_zeroed = true;
+    }
+    unsigned* done = s.misc.as<unsigned>();
+    k6_runs_bits_kernel<false><<<(unsigned)n_blocks, kWordsPerBlock, 0, stream>>>(
+        bits.lwords, bits.bwords, n_words, offsets_dev, n_reads, min_run, ext_left, ext_right, block_cnt, block_base, done,
+        nullptr, nullptr, 0);
+    CF_LAUNCHED();
+    k6_runs_bits_kernel<true><<<(unsigned)n_blocks, kWordsPerBlock, 0, stream>>>(
+        bits.lwords, bits.bwords, n_words, offsets_dev, n_reads, min_run, ext_left, ext_right, nullptr, block_base, nullptr,
+        run_start_global, intervals, capacity);
+    CF_LAUNCHED();
+    k6_read_offsets_kernel<<<(unsigned)ceil_div(n_reads + 1, 256), 256, 0, stream>>>(
+        run_start_global, block_base + n_blocks, offsets_dev, n_reads, interval_offsets, nullptr);
+    CF_LAUNCHED();
+    return CF_OK;
+}
+
 // ---------------------------------------------------------------- element-wise helpers
 __global__ void k6_threshold_kernel(const double* __restrict__ scores, int64_t n, double thr,
                                     int64_t* __restrict__ labels) {

@@ -63,9 +63,12 @@ bool tc_supported(const HostModel& hm);
 TcEngine* tc_create(const HostModel& hm);
 void tc_destroy(TcEngine* e);
 int tc_operand_format(const TcEngine* e);    // 0 = split bf16 (3 MMA passes), 1 = fp16 + e5m2 corrections (2 pass-equivalents)
+// bits != nullptr (networks with a GRU head): the head thresholds its own scores and ORs label bits into
+// bits->lwords (k6_bits_prepare) instead of writing probabilities - probs may then be nullptr.
+bool tc_can_emit_bits(const TcEngine* e);
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats,
                const float* xwin, WindowTable tab, int64_t n_tiles, float* probs,
-               cudaStream_t stream, Profiler* prof, bool want_logits = false);
+               cudaStream_t stream, Profiler* prof, bool want_logits = false, const LabelBits* bits = nullptr);
 
 int tc_selftest_f16e5(const float* a_dev, int K, int N, const float* w_host, int mode, float* out_dev, cudaStream_t stream);
 int tc_selftest_xproj(const float* a_dev, int64_t n_blocks, int K, const float* wx_host, const float* bias_host,

@@ -306,6 +306,7 @@ TcEngine* tc_create(const HostModel& hm) {
 }
 
 int tc_operand_format(const TcEngine* e) { return e ? e->fmt : 0; }
+bool tc_can_emit_bits(const TcEngine* e) { return e && !e->layers.empty(); }
 
 void tc_destroy(TcEngine* e) {
     if (!e) return;
@@ -1803,7 +1804,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const int64_t* __restrict__ src,
                const int32_t* __restrict__ valid, const int32_t* __restrict__ read,
-               const double* __restrict__ stats, int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits) {
+               const double* __restrict__ stats, int64_t tile0, int64_t n_rows, float* __restrict__ probs, int want_logits,
+               unsigned* __restrict__ lwords, double threshold) {
     __shared__ float logit[kWindow][kTileWindows + 1];
     const int64_t tile = blockIdx.x;
     if (tile * kTileWindows * kWindow >= n_rows) return;
@@ -1815,16 +1817,34 @@ tc_head_kernel(const float* __restrict__ head_part, int n_parts, float b, const 
         logit[t][w] = acc;
     }
     __syncthreads();
+    // 4480 = 35 * 128 = 17.5 * 256: the tail iteration runs whole warps, so the warp-level votes below are converged
     for (int i = threadIdx.x; i < kWindow * kTileWindows; i += blockDim.x) {
         const int w = i / kWindow, t = i % kWindow;
         const int64_t g = (tile0 + tile) * kTileWindows + w;
-        if (t >= valid[g]) continue;
-        float p = want_logits ? logit[t][w] : 1.f / (1.f + expf(-logit[t][w]));
-        if (stats) {
-            const double sc = stats[2 * read[g] + 1];
-            if (!(sc > 0.0)) p = nanf("");
+        const bool real = t < valid[g];
+        float p = 0.f;
+        if (real) {
+            p = want_logits ? logit[t][w] : 1.f / (1.f + expf(-logit[t][w]));
+            if (stats) {
+                const double sc = stats[2 * read[g] + 1];
+                if (!(sc > 0.0)) p = nanf("");
+            }
         }
-        probs[src[g] + t] = p;
+        if (!lwords) {
+            if (real) probs[src[g] + t] = p;
+            continue;
+        }
+        // label bits instead of probabilities (class_from_threshold, infer.py:128-138: the f32 score widened to
+        // double, >=): consecutive lanes hold consecutive samples, so a warp touches at most a few label words -
+        // lanes of one word OR their bits together and one of them issues the atomic
+        const bool hit = real && (double)p >= threshold;
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int64_t sidx = src[g] + t;
+            const unsigned peers = __match_any_sync(hits, (unsigned long long)(sidx >> 5));
+            const unsigned bits = __reduce_or_sync(peers, 1u << (sidx & 31));
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicOr(&lwords[sidx >> 5], bits);
+        }
     }
 }
 
@@ -1901,8 +1921,10 @@ static size_t tc_workspace_bytes(const TcEngine* e, int64_t tiles) {
 }
 
 int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const double* stats, const float* xwin,
-               WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream, Profiler* prof, bool want_logits) {
+               WindowTable tab, int64_t n_tiles, float* probs, cudaStream_t stream, Profiler* prof, bool want_logits,
+               const LabelBits* bits) {
     if (n_tiles <= 0) return CF_OK;
+    if (bits && (e->layers.empty() || want_logits)) { set_error("label-bit output needs a GRU head"); return CF_ERR_BAD_ARG; }
     if (!e->attr_done) {
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<32>::kSmem));
         CF_CUDA(cudaFuncSetAttribute(tc_xproj_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, XprojCfg<128>::kSmem));
@@ -2062,7 +2084,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
         } else {
             ProfScope ps(prof, KC_K5_HEAD, stream);
             tc_head_kernel<<<(unsigned)tiles, 256, 0, stream>>>(
-                head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs, want_logits ? 1 : 0);
+                head_part, head_parts, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs, want_logits ? 1 : 0,
+                bits ? bits->lwords : nullptr, bits ? bits->threshold : 0.0);
             CF_LAUNCHED();
         }
     }
