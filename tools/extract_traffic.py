@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
-"""Per-launch DRAM traffic of the main kernels from an `ncu --set full` report -> profiles/r1_traffic.json.
+"""Per-launch DRAM traffic of the main kernels from an `ncu --set full` report -> profiles/r2_traffic.json.
 
-    python tools/extract_traffic.py gpurun_out/r1_prof_main.ncu-rep
+    python tools/extract_traffic.py gpurun_out/r2_prof_main.ncu-rep
 
 bench.py reads the JSON to fill roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch,
-averaged over the captured launches of a kernel class).
+averaged over the captured launches of a kernel class).  The file is stamped with the git commit and with a
+fingerprint of catfish_b200/csrc/ (bench.source_fingerprint): bench.py refuses the figure when the kernels
+it times are not the ones the capture was taken from.
 """
 import csv
 import json
@@ -12,9 +14,7 @@ import os
 import subprocess
 import sys
 
-CLASSES = {"tc_gru_fused2_kernel": "k4_gru_recurrence", "tc_gru_fused_kernel": "k4_gru_recurrence",
-           "tc_conv4_kernel": "k2_conv_stack", "tc_conv3_kernel": "k2_conv_stack", "tc_conv2_kernel": "k2_conv_stack",
-           "tc_conv_kernel": "k2_conv_stack"}
+CLASSES = {"tc_gru_fused2_kernel": "k4_gru_recurrence", "tc_conv4_kernel": "k2_conv_stack", "tc_conv2_kernel": "k2_conv_stack"}
 UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 if __name__ == "__main__":
@@ -36,8 +36,16 @@ if __name__ == "__main__":
         b = float(r[ir]) * UNITS[units[ir]] + float(r[iw]) * UNITS[units[iw]]
         acc.setdefault(cls, []).append(b)
     res = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v)} for k, v in acc.items()}
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    sys.path.insert(0, root)
+    import bench
     res["source"] = os.path.basename(rep)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "r1_traffic.json")
+    res["source_sha1"] = bench.source_fingerprint()
+    res["commit"] = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() \
+        + ("+dirty" if subprocess.run(["git", "-C", root, "status", "--porcelain", "catfish_b200/csrc"], capture_output=True,
+                                       text=True).stdout.strip() else "")
+    res["samples_per_launch_note"] = "tools/profile_workload.py 96 reads: 12 182 812 samples, first engine pass = 2368 tiles"
+    path = os.path.join(root, "profiles", "r2_traffic.json")
     with open(path, "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res))
