@@ -668,7 +668,11 @@ template <int FMT>
 __global__ void __launch_bounds__(576, 1)
 tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ raw, const double* __restrict__ stats,
                 const float* __restrict__ xwin, const int64_t* __restrict__ src, const int32_t* __restrict__ valid,
-                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out) {
+                const int32_t* __restrict__ read, int64_t tile0, int n_tiles, __nv_bfloat16* __restrict__ y_out,
+                const float* __restrict__ head_w, float* __restrict__ head_part) {
+    // head_w != nullptr (ResNet-only network, resnet_class.py:23): the dense 32 -> 1 layer is taken in this epilogue -
+    // every thread writes the partial dot of its 16 channels to head_part[(block * 2 + half) * 128 + window] and the
+    // 128 B/sample operand block is never stored; tc_head_kernel adds the two halves.
     // FMT is the format of the OUTPUT (the first GRU layer's x operand; the engine uses bf16x3); inside the
     // stack every operand is split bf16 - the epilogue, not the tensor pipe, bounds this kernel and the bf16
     // split is the cheaper one.
@@ -909,7 +913,15 @@ tc_conv4_kernel(const uint8_t* __restrict__ params, const int16_t* __restrict__ 
                             v[i] = fmaxf(o.x, 0.f);
                             v[i + 1] = fmaxf(o.y, 0.f);
                         }
-                        store_a_row16_f<FMT>(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
+                        if (head_w) {
+                            float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2)
+                                acc2 = ffma2(make_float2(v[i], v[i + 1]), __ldg(reinterpret_cast<const float2*>(head_w + c0 + i)), acc2);
+                            head_part[(((size_t)tile * kWindow + t5) * 2 + ch) * 128 + row] = acc2.x + acc2.y;
+                        } else {
+                            store_a_row16_f<FMT>(reinterpret_cast<uint8_t*>(y_out) + ((size_t)tile * kWindow + t5) * kSliceBytes, row, c0, v);
+                        }
                     }
                 }
             }
@@ -1967,7 +1979,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
             const int grid = (int)std::min<int64_t>(tiles, e->n_sms);
             if (e->conv_nres == 2)
                 tc_conv4_kernel<0><<<grid, 576, kConv4Smem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
-                                                                     tab.read, tile0, (int)tiles, a0);
+                                                                     tab.read, tile0, (int)tiles, a0,
+                                                                     n_layers == 0 ? e->head_w : nullptr, n_layers == 0 ? head_part : nullptr);
             else
                 tc_conv2_kernel<1><<<grid, 288, kConvSmem, stream>>>(e->conv_params, raw, stats, xwin, tab.src, tab.valid,
                                                                      tab.read, tile0, (int)tiles, a0);
@@ -2075,7 +2088,14 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 a_in = yo;
             }
         }
-        if (n_layers == 0) {
+        if (n_layers == 0 && e->conv_nres == 2) {
+            // ResNet-only, two residual blocks: the conv kernel's epilogue already took the dense layer (two partial dots)
+            ProfScope ps(prof, KC_K5_HEAD, stream);
+            tc_head_kernel<<<(unsigned)tiles, 256, 0, stream>>>(
+                head_part, 2, e->head_b, tab.src, tab.valid, tab.read, raw ? stats : nullptr, tile0, rows, probs, want_logits ? 1 : 0,
+                nullptr, 0.0);
+            CF_LAUNCHED();
+        } else if (n_layers == 0) {
             // ResNet-only: dense on the conv output
             ProfScope ps(prof, KC_K5_HEAD, stream);
             tc_head_conv_kernel<<<(unsigned)tiles, 256, 0, stream>>>(

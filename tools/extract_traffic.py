@@ -40,7 +40,8 @@ if __name__ == "__main__":
     sys.path.insert(0, root)
     import bench
     res["source"] = os.path.basename(rep)
-    res["source_sha1"] = bench.source_fingerprint()
+    stamp = os.path.join(os.path.dirname(os.path.abspath(rep)), os.path.basename(rep).split("_")[0] + "_source_sha1.txt")
+    res["source_sha1"] = open(stamp).read().strip() if os.path.exists(stamp) else bench.source_fingerprint()    # recorded at capture time
     res["commit"] = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() \
         + ("+dirty" if subprocess.run(["git", "-C", root, "status", "--porcelain", "catfish_b200/csrc"], capture_output=True,
                                        text=True).stdout.strip() else "")

@@ -7,6 +7,7 @@
 set -u
 R=${1:-r2}
 mkdir -p gpurun_out
+python -c "import bench; print(bench.source_fingerprint())" > gpurun_out/${R}_source_sha1.txt      # which kernel sources the captures are of
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${R}_pytest_gpu.txt
 cat gpurun_out/${R}_pytest_gpu.txt
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_full.txt 2> gpurun_out/${R}_bench_full.err
