@@ -1395,9 +1395,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             uint64_t* b = &bars[8 * c];
             mbar_init(&b[Cfg::kBarG], 1);
             mbar_init(&b[Cfg::kBarC], 1);
-            mbar_init(&b[Cfg::kBarRh], 8);
-            mbar_init(&b[Cfg::kBarH], 8);
-            mbar_init(&b[Cfg::kBarCfree], 8);
+            mbar_init(&b[Cfg::kBarRh], 16);
+            mbar_init(&b[Cfg::kBarH], 16);
+            mbar_init(&b[Cfg::kBarCfree], 16);
             mbar_init(&b[Cfg::kBarXdone], 1);
         }
         for (int i = 0; i < Cfg::kStages; ++i) {
@@ -1594,211 +1594,182 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue
-        const int chain = warp >> 3;
-        const int q = warp & 3, hf = (warp >> 2) & 1;
+        // ------------------------------------------------------------ epilogue: 16 warps serve BOTH chains
+        // Thread = (window row, 16 of the 64 hidden units) of both chains.  A chain's step has two epilogue phases,
+        // R (reset gate -> r*h operand) after its gate MMAs and C (update gate, candidate, new state) after its
+        // candidate MMAs, and between them the warps would only wait for the tensor pipe.  With eight warps per
+        // chain that wait was idle time (per-step latency ~6 500 cycles whatever the x part cost); here all sixteen
+        // warps work through the phases of both chains in the fixed order
+        //     R(A, g)  C(B, g-1)  C(A, g)  R(B, g)
+        // so that every MMA group runs while the other chain's phase is being computed, each phase has half the
+        // values per thread, and the register budget holds the state of 2 x 16 units without spilling.
+        const int q = warp & 3, us = warp >> 2;
         const int row = q * 32 + lane;
-        const int j0 = hf * 32;
-        uint64_t* b = &bars[8 * chain];
-        const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + chain * 256 + j0;          // + gate * 64 + c0
-        const uint32_t t_ahi = tmem + ((uint32_t)(q * 32) << 16) + chain * 256 + 3 * kH + j0 / 2;   // + c0 / 2
-        const uint32_t t_alo = t_ahi + 32;
-        const float* hw = head_w ? head_w + dir * kH + j0 : nullptr;
-        const int my_tiles = tiles_of(chain);
-#ifndef CF_PRECISE_ACT
-        float2 h2[16], u2[16];                 // state and update gate of this thread's 32 units, as packed pairs
-#else
-        float h[32], u[32];
-#endif
-        int gs = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-#ifndef CF_PRECISE_ACT
+        const int j0 = us * 16;
+        const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
+        const int tot[2] = {tiles_of(0) * kWindow, tiles_of(1) * kWindow};
+        float2 h2[2][8];                       // state of this thread's 16 units, per chain, as packed pairs
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h2[j] = make_float2(0.f, 0.f);
-#else
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = 0.f;
+            for (int j = 0; j < 8; ++j) h2[c][j] = make_float2(0.f, 0.f);
+
+        // activation argument bias (+ x_t * w for the scalar-input layer), 4 consecutive columns
+        auto bias4 = [&](int idx, float xv) -> float4 {
+            float4 b4 = *reinterpret_cast<const float4*>(bias_s + idx);
+            if (kNoX) {
+                const float4 w4 = *reinterpret_cast<const float4*>(bias_s + 192 + idx);
+                b4.x = fmaf(xv, w4.x, b4.x); b4.y = fmaf(xv, w4.y, b4.y); b4.z = fmaf(xv, w4.z, b4.z); b4.w = fmaf(xv, w4.w, b4.w);
+            }
+            return b4;
+        };
+        auto sig4 = [&](const uint32_t* a, float4 b4, float2& o0, float2& o1) {
+#ifndef CF_PRECISE_ACT
+            o0 = sigmoid_zb2(make_float2(__uint_as_float(a[0]), __uint_as_float(a[1])), make_float2(b4.x, b4.y));
+            o1 = sigmoid_zb2(make_float2(__uint_as_float(a[2]), __uint_as_float(a[3])), make_float2(b4.z, b4.w));
+#else
+            float z[4] = {__uint_as_float(a[0]) + b4.x, __uint_as_float(a[1]) + b4.y, __uint_as_float(a[2]) + b4.z, __uint_as_float(a[3]) + b4.w};
+            float y[4];
+            sigmoid4_z(z, y);
+            o0 = make_float2(y[0], y[1]);
+            o1 = make_float2(y[2], y[3]);
 #endif
+        };
+        auto tanh4v = [&](const uint32_t* a, float4 b4, float2& o0, float2& o1) {
+#ifndef CF_PRECISE_ACT
+            o0 = tanh_zb2(make_float2(__uint_as_float(a[0]), __uint_as_float(a[1])), make_float2(b4.x, b4.y));
+            o1 = tanh_zb2(make_float2(__uint_as_float(a[2]), __uint_as_float(a[3])), make_float2(b4.z, b4.w));
+#else
+            float z[4] = {__uint_as_float(a[0]) + b4.x, __uint_as_float(a[1]) + b4.y, __uint_as_float(a[2]) + b4.z, __uint_as_float(a[3]) + b4.w};
+            float y[4];
+            tanh4_z(z, y);
+            o0 = make_float2(y[0], y[1]);
+            o1 = make_float2(y[2], y[3]);
+#endif
+        };
+        // zero state operand of a chain's next tile
+        auto begin_tile = [&](int c) {
+            const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
+            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h2[c][j] = make_float2(0.f, 0.f);
+            tmem_st8_u32(t_ahi, z);
+            tmem_st8_u32(t_alo, z);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[8 * c + Cfg::kBarH]);
+        };
+        // ---- phase R of chain c, step gs: reset gate -> r*h operand
+        auto phase_r = [&](int c, int gs) {
+            uint64_t* b = &bars[8 * c];
+            const uint32_t t_acc = t_row + c * 256 + j0;
+            const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
+            const float xv = kNoX ? __ldg(x_scalar + blk_of(c, gs) * 128 + row) : 0.f;
+            mbar_wait(&b[Cfg::kBarG], gs & 1);
+            tc_fence_after_sync();
+            uint32_t ar[16];
+            tmem_ld16_nowait(t_acc, ar);
+            tmem_ld_wait();
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                float2 r0, r1;
+                sig4(ar + i, bias4(j0 + i, xv), r0, r1);
+                const float2 p0 = fmul2(r0, h2[c][i >> 1]), p1 = fmul2(r1, h2[c][(i >> 1) + 1]);
+                split4<FMT>(p0.x, p0.y, p1.x, p1.y, i, hi, lo);
+            }
+            tmem_st8_u32(t_ahi, hi);
+            tmem_st8_u32(t_alo, lo);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b[Cfg::kBarRh]);
+        };
+        // ---- phase C of chain c, step gs: update gate (while the candidate MMAs finish), candidate, h = c + u (h - c)
+        auto phase_c = [&](int c, int gs) {
+            uint64_t* b = &bars[8 * c];
+            const uint32_t t_acc = t_row + c * 256 + j0;
+            const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
+            const size_t blk = blk_of(c, gs);
+            const int s = gs % kWindow;
+            const float xv = kNoX ? __ldg(x_scalar + blk * 128 + row) : 0.f;
+            float2 u2[8];
             {
-                const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                tmem_st8_u32(t_ahi, z);
-                tmem_st8_u32(t_ahi + 8, z);
-                tmem_st8_u32(t_alo, z);
-                tmem_st8_u32(t_alo + 8, z);
+                uint32_t au[16];
+                tmem_ld16_nowait(t_acc + kH, au);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) sig4(au + i, bias4(kH + j0 + i, xv), u2[i >> 1], u2[(i >> 1) + 1]);
+            }
+            mbar_wait(&b[Cfg::kBarC], gs & 1);
+            tc_fence_after_sync();
+            uint32_t ac[16];
+            tmem_ld16_nowait(t_acc + 2 * kH, ac);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b[Cfg::kBarCfree]);      // accumulators drained: next x part may start
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                float2 c0v, c1v;
+                tanh4v(ac + i, bias4(2 * kH + j0 + i, xv), c0v, c1v);
+                float2& ha = h2[c][i >> 1];
+                float2& hb = h2[c][(i >> 1) + 1];
+                ha = ffma2(u2[i >> 1], ffma2(c0v, splat2(-1.f), ha), c0v);
+                hb = ffma2(u2[(i >> 1) + 1], ffma2(c1v, splat2(-1.f), hb), c1v);
+                split4<FMT>(ha.x, ha.y, hb.x, hb.y, i, hi, lo);
+            }
+            const bool more = gs + 1 < tot[c];
+            if (s + 1 < kWindow) {                       // hand h to the next step before the global stores
+                tmem_st8_u32(t_ahi, hi);
+                tmem_st8_u32(t_alo, lo);
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
             }
-            for (int s = 0; s < kWindow; ++s, ++gs) {
-                const uint32_t par = gs & 1;
-                const size_t blk = blk_of(chain, gs);
-                // scalar layer input (RNN-only layer 0): activation argument = acc + (b + x_t w), one extra FMA per value
-                const float xv = kNoX ? __ldg(x_scalar + blk * 128 + row) : 0.f;
-                auto bias4 = [&](int idx) -> float4 {
-                    float4 b4 = *reinterpret_cast<const float4*>(bias_s + idx);
-                    if (kNoX) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(bias_s + 192 + idx);
-                        b4.x = fmaf(xv, w4.x, b4.x); b4.y = fmaf(xv, w4.y, b4.y); b4.z = fmaf(xv, w4.z, b4.z); b4.w = fmaf(xv, w4.w, b4.w);
-                    }
-                    return b4;
-                };
-                // ---- reset gate -> r*h operand
-                mbar_wait(&b[Cfg::kBarG], par);
-                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 50);
-                tc_fence_after_sync();
-                {
-                    uint32_t ar[32];
-                    tmem_ld16_nowait(t_acc, ar);
-                    tmem_ld16_nowait(t_acc + 16, ar + 16);
-                    tmem_ld_wait();
+            if (y_out && !(kExp & 4)) {
+                // next layer's A operand, in the NEXT layer's operand format (a second split when it differs)
+                if (FMT_OUT != FMT) {
 #pragma unroll
-                    for (int c0 = 0; c0 < 32; c0 += 16) {
-                        uint32_t hi[8], lo[8];
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 b4 = bias4(j0 + c0 + i);
-#ifndef CF_PRECISE_ACT
-                            const float2 r0 = sigmoid_zb2(make_float2(__uint_as_float(ar[c0 + i]), __uint_as_float(ar[c0 + i + 1])), make_float2(b4.x, b4.y));
-                            const float2 r1 = sigmoid_zb2(make_float2(__uint_as_float(ar[c0 + i + 2]), __uint_as_float(ar[c0 + i + 3])), make_float2(b4.z, b4.w));
-                            const float2 p0 = fmul2(r0, h2[(c0 + i) >> 1]), p1 = fmul2(r1, h2[((c0 + i) >> 1) + 1]);
-                            split4<FMT>(p0.x, p0.y, p1.x, p1.y, i, hi, lo);
-#else
-                            float r[4];
-                            float z[4];
-                            z[0] = __uint_as_float(ar[c0 + i]) + b4.x; z[1] = __uint_as_float(ar[c0 + i + 1]) + b4.y;
-                            z[2] = __uint_as_float(ar[c0 + i + 2]) + b4.z; z[3] = __uint_as_float(ar[c0 + i + 3]) + b4.w;
-                            sigmoid4_z(z, r);
-                            split4<FMT>(r[0] * h[c0 + i], r[1] * h[c0 + i + 1], r[2] * h[c0 + i + 2], r[3] * h[c0 + i + 3], i, hi, lo);
-#endif
-                        }
-                        tmem_st8_u32(t_ahi + c0 / 2, hi);
-                        tmem_st8_u32(t_alo + c0 / 2, lo);
-                    }
+                    for (int i = 0; i < 16; i += 4)
+                        split4<FMT_OUT>(h2[c][i >> 1].x, h2[c][i >> 1].y, h2[c][(i >> 1) + 1].x, h2[c][(i >> 1) + 1].y, i, hi, lo);
                 }
-                tmem_st_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b[Cfg::kBarRh]);
-                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 51);
-                // ---- update gate while the candidate MMA runs
-                {
-                    uint32_t au[32];
-                    tmem_ld16_nowait(t_acc + kH, au);
-                    tmem_ld16_nowait(t_acc + kH + 16, au + 16);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = bias4(kH + j0 + i);
-#ifndef CF_PRECISE_ACT
-                        u2[i >> 1] = sigmoid_zb2(make_float2(__uint_as_float(au[i]), __uint_as_float(au[i + 1])), make_float2(b4.x, b4.y));
-                        u2[(i >> 1) + 1] = sigmoid_zb2(make_float2(__uint_as_float(au[i + 2]), __uint_as_float(au[i + 3])), make_float2(b4.z, b4.w));
-#else
-                        float z[4];
-                        z[0] = __uint_as_float(au[i]) + b4.x; z[1] = __uint_as_float(au[i + 1]) + b4.y;
-                        z[2] = __uint_as_float(au[i + 2]) + b4.z; z[3] = __uint_as_float(au[i + 3]) + b4.w;
-                        sigmoid4_z(z, u + i);
-#endif
-                    }
-                }
-                // ---- candidate, new state h = c + u (h - c)
-                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 52);
-                mbar_wait(&b[Cfg::kBarC], par);
-                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 53);
-                tc_fence_after_sync();
-                uint32_t ac[32];
-                tmem_ld16_nowait(t_acc + 2 * kH, ac);
-                tmem_ld16_nowait(t_acc + 2 * kH + 16, ac + 16);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b[Cfg::kBarCfree]);      // accumulators drained: next x part may start
-                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 54);
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = bias4(2 * kH + j0 + i);
-#ifndef CF_PRECISE_ACT
-                    {
-                        // h = c + u (h - c), two units per instruction
-                        const float2 c0v = tanh_zb2(make_float2(__uint_as_float(ac[i]), __uint_as_float(ac[i + 1])), make_float2(b4.x, b4.y));
-                        const float2 c1v = tanh_zb2(make_float2(__uint_as_float(ac[i + 2]), __uint_as_float(ac[i + 3])), make_float2(b4.z, b4.w));
-                        float2& ha = h2[i >> 1];
-                        float2& hb = h2[(i >> 1) + 1];
-                        ha = ffma2(u2[i >> 1], ffma2(c0v, splat2(-1.f), ha), c0v);
-                        hb = ffma2(u2[(i >> 1) + 1], ffma2(c1v, splat2(-1.f), hb), c1v);
-                        split4<FMT>(ha.x, ha.y, hb.x, hb.y, i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
-                    }
-#else
-                    float cv[4];
-                    float z[4];
-                    z[0] = __uint_as_float(ac[i]) + b4.x; z[1] = __uint_as_float(ac[i + 1]) + b4.y;
-                    z[2] = __uint_as_float(ac[i + 2]) + b4.z; z[3] = __uint_as_float(ac[i + 3]) + b4.w;
-                    tanh4_z(z, cv);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) h[i + k] = fmaf(u[i + k], h[i + k] - cv[k], cv[k]);
-                    split4<FMT>(h[i], h[i + 1], h[i + 2], h[i + 3], i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
-#endif
-                }
-                tmem_st8_u32(t_ahi, hi);
-                tmem_st8_u32(t_ahi + 8, hi + 8);
-                tmem_st8_u32(t_alo, lo);
-                tmem_st8_u32(t_alo + 8, lo + 8);
-                tmem_st_wait();
-                tc_fence_before_sync();
-                if (s + 1 < kWindow) {                   // hand h to the next step before the global stores
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
-                }
-                if ((warp & 7) == 0 && lane == 0) CF_TR(2 + chain, gs, 55);
-                if (y_out && !(kExp & 4)) {
-                    // next layer's A operand: block {plane 0, plane 1} x [16][128][8], features dir*64 + j,
-                    // in the NEXT layer's operand format (a second split when it differs from this layer's)
-                    if (FMT_OUT != FMT) {
-#ifndef CF_PRECISE_ACT
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            split4<FMT_OUT>(h2[i >> 1].x, h2[i >> 1].y, h2[(i >> 1) + 1].x, h2[(i >> 1) + 1].y, i & 15,
-                                            hi + (i >> 4) * 8, lo + (i >> 4) * 8);
-#else
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            split4<FMT_OUT>(h[i], h[i + 1], h[i + 2], h[i + 3], i & 15, hi + (i >> 4) * 8, lo + (i >> 4) * 8);
-#endif
-                    }
-                    // hi[] = main words of the 32 values; lo[] = per 16 values: 4 words of remainder bytes, then the 4
-                    // words of hi bytes (f16e5) / 8 words of bf16 remainders (split bf16)
-                    uint8_t* yb = reinterpret_cast<uint8_t*>(y_out) + blk * gru_out_block_bytes(FMT_OUT);
-                    uint8_t* ym = yb + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 16;
-#pragma unroll
-                    for (int kg = 0; kg < 4; ++kg)
-                        *reinterpret_cast<uint4*>(ym + kg * 2048) = make_uint4(hi[4 * kg], hi[4 * kg + 1], hi[4 * kg + 2], hi[4 * kg + 3]);
-                    if (FMT_OUT == kFmtF16E5) {
-                        // compact form: only the remainder bytes travel (one 2 KB slab per K = 16 chunk of the block)
-                        uint8_t* yl = yb + 128 * 2 * kH * 2 + ((size_t)(dir * kH + j0) / 16 * 128 + row) * 16;
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-                            *reinterpret_cast<uint4*>(yl + c * 2048) = make_uint4(lo[8 * c], lo[8 * c + 1], lo[8 * c + 2], lo[8 * c + 3]);
-                    } else {
-#pragma unroll
-                        for (int kg = 0; kg < 4; ++kg)
-                            *reinterpret_cast<uint4*>(ym + 128 * 2 * kH * 2 + kg * 2048) = make_uint4(lo[4 * kg], lo[4 * kg + 1], lo[4 * kg + 2], lo[4 * kg + 3]);
-                    }
-                }
-                if (head_part) {
-#ifndef CF_PRECISE_ACT
-                    float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc2 = ffma2(h2[i], __ldg(reinterpret_cast<const float2*>(hw) + i), acc2);
-                    const float acc = acc2.x + acc2.y;
-#else
-                    float acc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc = fmaf(h[i], __ldg(hw + i), acc);
-#endif
-                    head_part[((blk * 2 + dir) * 2 + hf) * 128 + row] = acc;
+                // hi[] = main words of the 16 values; lo[] = 4 words of remainder bytes then 4 of hi bytes (f16e5) /
+                // 8 words of bf16 remainders (split bf16)
+                uint8_t* yb = reinterpret_cast<uint8_t*>(y_out) + blk * gru_out_block_bytes(FMT_OUT);
+                uint8_t* ym = yb + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 16;
+                *reinterpret_cast<uint4*>(ym) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(ym + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                if (FMT_OUT == kFmtF16E5) {
+                    // compact form: only the remainder bytes travel (one 2 KB slab per K = 16 chunk of the block)
+                    *reinterpret_cast<uint4*>(yb + 128 * 2 * kH * 2 + ((size_t)(dir * kH + j0) / 16 * 128 + row) * 16) =
+                        make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                } else {
+                    *reinterpret_cast<uint4*>(ym + 128 * 2 * kH * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(ym + 128 * 2 * kH * 2 + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
             }
+            if (head_part) {
+                const float* hw = head_w + dir * kH + j0;
+                float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc2 = ffma2(h2[c][i], __ldg(reinterpret_cast<const float2*>(hw) + i), acc2);
+                head_part[((blk * 2 + dir) * 4 + us) * 128 + row] = acc2.x + acc2.y;
+            }
+            if (s + 1 == kWindow && more) begin_tile(c);      // the chain's next tile starts from a zero state
+        };
+
+        if (tot[0] > 0) begin_tile(0);
+        if (tot[1] > 0) begin_tile(1);
+        const int g_end = tot[0] > tot[1] ? tot[0] : tot[1];
+        for (int g = 0; g <= g_end; ++g) {
+            if (g < tot[0]) phase_r(0, g);
+            if (g >= 1 && g - 1 < tot[1]) phase_c(1, g - 1);
+            if (g < tot[0]) phase_c(0, g);
+            if (g < tot[1]) phase_r(1, g);
         }
     }
     tc_fence_before_sync();
@@ -2053,7 +2024,7 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                     e->trace_done = true;
                 }
                 a_in = yo;
-                head_parts = 4;
+                head_parts = 8;
                 continue;
             }
             head_parts = 2;
