@@ -1520,7 +1520,6 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
                     const uint32_t st = cn % Cfg::kStages;
                     mbar_wait(&bars[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
-                    if (lane == 0) CF_TR(c, gs, 60 + kk);
                     tc_fence_after_sync();
                     const uint32_t a0 = s0 + Cfg::kRing + st * 8192;
                     if (kE5) {
@@ -1538,7 +1537,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                         }
                     }
                     umma_commit_pred(&bars[Cfg::kBarEmpty + st], elected);
-                    if (lane == 0) CF_TR(c, gs, 20 + kk);
+                    if (kk == Cfg::kChunks - 1 && lane == 0) CF_TR(c, gs, 27);
                 }
                 if (!kNoX && lane == 0) mbar_arrive(&b[Cfg::kBarXdone]);
                 // state part of the gates
@@ -1666,7 +1665,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             const uint32_t t_acc = t_row + c * 256 + j0;
             const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
             const float xv = kNoX ? __ldg(x_scalar + blk_of(c, gs) * 128 + row) : 0.f;
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 49);
             mbar_wait(&b[Cfg::kBarG], gs & 1);
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 50);
             tc_fence_after_sync();
             uint32_t ar[16];
             tmem_ld16_nowait(t_acc, ar);
@@ -1685,6 +1686,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&b[Cfg::kBarRh]);
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 51);
         };
         // ---- phase C of chain c, step gs: update gate (while the candidate MMAs finish), candidate, h = c + u (h - c)
         auto phase_c = [&](int c, int gs) {
@@ -1702,7 +1704,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) sig4(au + i, bias4(kH + j0 + i, xv), u2[i >> 1], u2[(i >> 1) + 1]);
             }
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 52);
             mbar_wait(&b[Cfg::kBarC], gs & 1);
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 53);
             tc_fence_after_sync();
             uint32_t ac[16];
             tmem_ld16_nowait(t_acc + 2 * kH, ac);
@@ -1730,6 +1734,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b[Cfg::kBarH]);
             }
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 55);
             if (y_out && !(kExp & 4)) {
                 // next layer's A operand, in the NEXT layer's operand format (a second split when it differs)
                 if (FMT_OUT != FMT) {
@@ -1760,6 +1765,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 head_part[((blk * 2 + dir) * 4 + us) * 128 + row] = acc2.x + acc2.y;
             }
             if (s + 1 == kWindow && more) begin_tile(c);      // the chain's next tile starts from a zero state
+            if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 56);
         };
 
         if (tot[0] > 0) begin_tile(0);

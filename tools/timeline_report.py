@@ -6,8 +6,9 @@
 
 Regions 0/1 = MMA issuer of chain 0/1, 2/3 = epilogue of chain 0/1.  Tags (tc_engine.cu, CF_TR):
 issuer 10 x-part start, 60+kk chunk kk's data there, 20+kk chunk kk issued, 30 h ready, 31 gate MMAs issued, 40 r*h ready, 41 candidate
-MMAs issued; epilogue 50 gates landed, 51 r*h handed over, 52 update gate done, 53 candidate landed,
-54 accumulators drained, 55 new state handed over.
+MMAs issued; epilogue (warp 0, which serves both chains; regions 2/3 = its work for chain 0/1) 49 phase R entered,
+50 gates landed, 51 r*h handed over | 52 phase C: update gate done, 53 candidate landed, 55 new state handed over,
+56 phase C left (layer output stored).
 """
 import sys
 from collections import defaultdict
