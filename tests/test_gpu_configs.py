@@ -74,3 +74,69 @@ def test_config2_resnet_only_large_batch_subset_vs_oracle():
     # batch invariance: the same windows alone give the same bits
     alone = m.infer(x[sel])
     np.testing.assert_array_equal(alone, got)
+
+
+def test_rnn_only_fused_layer0_at_scale_vs_fp32_engine():
+    """RNN-only network through the fused layer kernel (scalar input folded into the epilogue, f16e5 operands in
+    every layer) on a ragged batch of several thousand tiles, against the fp32 CUDA-core engine."""
+    w = weights.random_init("RNN", seed=23, layer_size=64, n_layers=3)
+    fast = _build("RNN", w)
+    assert fast.resolved_engine == "tcgen05" and fast.operand_format == "f16e5"
+    full = dict(weights.SHIPPED_HPARAMS)
+    slow = neural_network.build_model("RNN", engine="simt", **full)
+    slow.set_weights(w)
+    reads = synth.synth_reads(synth.ragged_lengths(60, 20_000, 60_000, seed=8), base_seed=2300)
+    h1, l1, s1 = infer.infer_reads(reads, fast, return_scores=True)
+    h2, l2, s2 = infer.infer_reads(reads, slow, return_scores=True)
+    assert l1 == l2
+    worst = max(float(np.abs(a - b).max()) for a, b in zip(s1, s2))
+    assert worst < PROB_TOL, worst
+    for a, b, sa, sb in zip(h1, h2, s1, s2):
+        if a != b:
+            flip = (sa.astype(np.float64) >= 0.5) != (sb.astype(np.float64) >= 0.5)
+            assert flip.any() and np.all(allowed_label_flips(sb.astype(np.float64))[flip])
+
+
+def test_label_bit_path_equals_probability_path(shipped_weights):
+    """With no probabilities requested the head kernel thresholds its own scores into label bits and the interval
+    caller starts from those; with probabilities requested it reads them back from HBM.  Same intervals, bit for
+    bit, for several thresholds, incl. a constant read (NaN scores), one-sample reads and 35-divisible lengths."""
+    m = _build("ResNetRNN", shipped_weights)
+    lengths = [1, 34, 35, 36, 70, 4480, 4481, 31, 64, 10000, 33333]
+    reads = synth.synth_reads(lengths, base_seed=77) + [np.full(300, 5, np.int16)]
+    reads += synth.synth_reads(synth.ragged_lengths(40, 3000, 90_000, seed=4), base_seed=610)
+    raw, off = synth.concat_reads(reads)
+    for thr, min_run, el, er in ((0.5, 15, 11, 16), (0.3, 1, 0, 0), (0.9, 40, 3, 7)):
+        iv_b, ioff_b = infer.infer_concatenated(raw, off, m, threshold=thr, min_run=min_run, extension_left=el,
+                                                extension_right=er)
+        iv_p, ioff_p, scores = infer.infer_concatenated(raw, off, m, threshold=thr, min_run=min_run, extension_left=el,
+                                                        extension_right=er, return_scores=True)
+        np.testing.assert_array_equal(ioff_b, ioff_p)
+        np.testing.assert_array_equal(iv_b, iv_p)
+        # and both are the reference's post-processing of the returned scores
+        for r in (0, 3, 9, 11, 20):
+            s = scores[off[r]:off[r + 1]].astype(np.float64)
+            labels = postprocess.correct_short(postprocess.class_from_threshold(s, thr), min_run)
+            assert iv_b[ioff_b[r]:ioff_b[r + 1]].tolist() == postprocess.hp_in_pred(labels, el, er)
+
+
+def test_sharded_job_single_rank_equals_batch_call(shipped_weights):
+    """sharding.infer_reads_sharded on one rank (the N = 1 job of bench.py): small batches + CSR merge give
+    exactly the per-read results of one call, through a lazy read sequence and the lazy result views."""
+    from catfish_b200 import sharding
+    m = _build("ResNetRNN", shipped_weights)
+    lengths = synth.ragged_lengths(37, 500, 30_000, seed=12)
+    reads = synth.synth_reads(lengths, base_seed=1200)
+    want_h, want_l = infer.infer_reads(reads, m)
+
+    class Lazy(object):
+        def __len__(self):
+            return len(reads)
+
+        def __getitem__(self, i):
+            return reads[int(i)]
+
+    hps, lens = sharding.infer_reads_sharded(Lazy(), m, 0, 1, batch_reads=8, lengths=lengths)
+    assert lens == want_l and len(hps) == len(reads)
+    assert all(a == b for a, b in zip(hps, want_h))
+    assert hps[5].tolist() == want_h[5].tolist() and hps[1:3][1] == want_h[2]
