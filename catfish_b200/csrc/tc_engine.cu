@@ -1359,7 +1359,10 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                      long long* __restrict__ trace, const float* __restrict__ x_scalar, const float* __restrict__ wx_scalar) {
     using Cfg = GruF2Cfg<KX>;
     constexpr bool kNoX = Cfg::kNoX;
-    // debug timeline (CF_TC_TRACE): block 0 records (tag, SM clock) pairs for steps 36..39 of each role
+    // debug timeline (build with -DCF_TRACE_PROBES, run with CF_TC_TRACE=<file>): block 0 records (tag, SM clock)
+    // pairs for steps 36..39 of each role.  Compiled out of the shipped library: fourteen probes per step are
+    // ~8 % of the epilogue's instruction stream even when they record nothing.
+#ifdef CF_TRACE_PROBES
     int tr_n = 0;
 #define CF_TR(region, step, tag)                                                                   \
     do {                                                                                           \
@@ -1371,6 +1374,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             ++tr_n;                                                                                \
         }                                                                                          \
     } while (0)
+#else
+#define CF_TR(region, step, tag) do { } while (0)
+#endif
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][8] per chain, ring full / empty, w_bar
     uint64_t* w_bar = &bars[Cfg::kBarW];
@@ -1608,6 +1614,10 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
         const int tot[2] = {tiles_of(0) * kWindow, tiles_of(1) * kWindow};
         float2 h2[2][8];                       // state of this thread's 16 units, per chain, as packed pairs
+        // position of each chain inside its tile and the tile's first block, advanced step by step (no division)
+        int spos[2] = {0, 0};
+        size_t tile_blk[2] = {(size_t)(slot * 2) * kWindow, (size_t)(slot * 2 + 1) * kWindow};
+        auto cur_blk = [&](int c) -> size_t { return tile_blk[c] + (dir ? kWindow - 1 - spos[c] : spos[c]); };
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1664,7 +1674,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             uint64_t* b = &bars[8 * c];
             const uint32_t t_acc = t_row + c * 256 + j0;
             const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
-            const float xv = kNoX ? __ldg(x_scalar + blk_of(c, gs) * 128 + row) : 0.f;
+            const float xv = kNoX ? __ldg(x_scalar + cur_blk(c) * 128 + row) : 0.f;
             if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 49);
             mbar_wait(&b[Cfg::kBarG], gs & 1);
             if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 50);
@@ -1693,8 +1703,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             uint64_t* b = &bars[8 * c];
             const uint32_t t_acc = t_row + c * 256 + j0;
             const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
-            const size_t blk = blk_of(c, gs);
-            const int s = gs % kWindow;
+            const size_t blk = cur_blk(c);
+            const int s = spos[c];
             const float xv = kNoX ? __ldg(x_scalar + blk * 128 + row) : 0.f;
             float2 u2[8];
             {
@@ -1764,7 +1774,13 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 for (int i = 0; i < 8; ++i) acc2 = ffma2(h2[c][i], __ldg(reinterpret_cast<const float2*>(hw) + i), acc2);
                 head_part[((blk * 2 + dir) * 4 + us) * 128 + row] = acc2.x + acc2.y;
             }
-            if (s + 1 == kWindow && more) begin_tile(c);      // the chain's next tile starts from a zero state
+            if (s + 1 == kWindow) {
+                spos[c] = 0;
+                tile_blk[c] += (size_t)stride * kWindow;
+                if (more) begin_tile(c);                 // the chain's next tile starts from a zero state
+            } else {
+                spos[c] = s + 1;
+            }
             if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 56);
         };
 
