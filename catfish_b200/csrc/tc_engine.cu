@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "model.cuh"
 #include "tc_ptx.cuh"
@@ -1320,20 +1321,27 @@ tc_gru_kernel(const __nv_bfloat16* __restrict__ wh, const float* __restrict__ xp
 // operand h / r*h no longer lives in shared memory: the epilogue writes it (packed, in the operand
 // format FMT) into tensor memory with tcgen05.st and the state-part MMAs read A from TMEM (".ts" form).
 // TMEM per chain (256 columns): gates accumulator 0..127, candidate 128..191, A plane 0 192..223,
-// A plane 1 224..255.  Shared memory: weights (147 KB) + ONE 10-stage x ring (80 KB) that both chains
+// A plane 1 224..255.  Shared memory: weights (147 KB) + ONE x ring (8 stages of 8 KB for a 128-wide input = one
+// entry per turn, 10 stages for a 32-wide one) that both chains
 // consume in the fixed order (step 0, chain 0), (step 0, chain 1), (step 1, chain 0), ...: with a private
 // 5-stage ring per chain only 5 of a step's 8 chunks could be requested before the step's x part began,
 // so the last three arrived a full HBM latency later (x part 4 400-4 900 cycles for 1 536 of MMA time);
 // in the shared ring a step's chunks are all requested while the OTHER chain's x part runs.
-//   warps 0-7 / 8-15 : epilogue of chain 0 / 1; thread = (window, half of the hidden units)
+//   warps 0-15       : epilogue of BOTH chains; thread = (window, 16 of the hidden units)
 //   warp 16 / 17     : MMA issuer of chain 0 / 1 (x part, then state part of gates, then of candidate)
 //   warp 18          : lane 0 = producer (weights once, then the x ring)
-//   warp 19          : f16e5 input only - rebuilds each landed chunk's hi-byte slab from its main plane (the
-//                      compact HBM form carries 3 of the 4 operand bytes; tc_ptx.cuh) and hands the stage on
+//   warp 19 / 20     : f16e5 input only - rebuild each landed chunk's hi-byte slab from its main plane (the
+//                      compact HBM form carries 3 of the 4 operand bytes; tc_ptx.cuh) and hand the stage on;
+//                      even / odd ring stages
+//   warps 21-23      : idle (they exist so that the warpgroup 20-23 can hand its registers back)
+// Registers: launched with 80 per thread; the service warpgroups (16-23) shrink to 48 and the epilogue
+// warpgroups (0-15) grow to 96 with setmaxnreg, the role code sits inside the branch that executed it.
 template <int KX> struct GruF2Cfg {
     static constexpr bool kNoX = KX == 1;                                 // scalar layer input: x part added in the epilogue
     static constexpr int kChunks = KX / 16;
-    static constexpr int kStages = 10;                                    // ONE ring shared by both chains (see the producer)
+    // ONE ring shared by both chains (see the producer).  128-wide input: 8 stages = one entry per turn, which makes
+    // every stage index in the issue loop a compile-time constant (see the issuer)
+    static constexpr int kStages = KX == 128 ? 8 : 10;
     static constexpr uint32_t kWx = 0;                                   // {hi, lo} x [KX/8][192][8]  (r | u | c)
     static constexpr uint32_t kWgh = kWx + (kNoX ? 0u : 2u * KX * kNX * 2);
     static constexpr uint32_t kWch = kWgh + 2u * kH * 128 * 2;
@@ -1349,7 +1357,14 @@ template <int KX> struct GruF2Cfg {
 // Bytes of one (tile, t) block of a 128-wide layer output in HBM: split bf16 = two 16-bit planes; f16e5 =
 // fp16 main plane [16][128][8 x 2 B] + remainder bytes [8 chunks][128][16 B] (the hi bytes are rebuilt by the reader).
 __host__ __device__ constexpr uint32_t gru_out_block_bytes(int fmt) { return fmt == kFmtF16E5 ? 49152u : 65536u; }
-constexpr int kGruF2Threads = 640;
+// 24 warps = six per sub-partition.  Launched with 80 registers per thread; the two service warpgroups (16-23) give
+// theirs back (setmaxnreg) and the four epilogue warpgroups grow to 96: 4 x 96 + 2 x 48 = 480 = 6 x 80 per lane.
+constexpr int kGruF2Threads = 768;
+constexpr int kGruF2Converters = 2;               // warps 19.. rebuilding hi-byte slabs; must divide the ring's stages
+constexpr int kGruF2EpiRegs = 96, kGruF2ServiceRegs = 48;
+#ifndef CF_L2_PREFETCH
+#define CF_L2_PREFETCH 1
+#endif
 
 template <int KX, int FMT, int FMT_OUT>
 __global__ void __launch_bounds__(kGruF2Threads, 1)
@@ -1367,15 +1382,18 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 #define CF_TR(region, step, tag)                                                                   \
     do {                                                                                           \
         if (trace && blockIdx.x == 0 && (step) >= 36 && (step) < 40 && tr_n < 200) {               \
-            long long gt_;                                                                         \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                \
-            trace[((region) * 200 + tr_n) * 2] = (tag) + 1000 * (gt_ % 100000000LL);               \
+            trace[((region) * 200 + tr_n) * 2] = (tag) + 1000 * (long long)(step);                      \
             trace[((region) * 200 + tr_n) * 2 + 1] = clock64();                                    \
             ++tr_n;                                                                                \
         }                                                                                          \
     } while (0)
 #else
 #define CF_TR(region, step, tag) do { } while (0)
+#endif
+#ifdef CF_TRACE_CHUNKS        // per-chunk probes of the x ring (issuer, converter, producer): they slow the ring itself
+#define CF_TRC(region, step, tag) CF_TR(region, step, tag)
+#else
+#define CF_TRC(region, step, tag) do { } while (0)
 #endif
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);     // [2][8] per chain, ring full / empty, w_bar
@@ -1428,6 +1446,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
+    if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGruF2ServiceRegs));
     if (warp == 18) {
         // ------------------------------------------------------------ producer: weights once, then the shared x ring
         if (lane == 0) {
@@ -1438,7 +1458,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 bulk_g2s(smem + off, wsrc + off, n, w_bar);
             }
             // input block in HBM: split bf16 = two planes of 128 * KX * 2 bytes; compact f16e5 = main plane + KX / 16
-            // remainder slabs of 2 KB (the chunk's hi slab, the last 2 KB of the stage, is filled by warp 19)
+            // remainder slabs of 2 KB (the chunk's hi slab, the last 2 KB of the stage, is filled by warps 19 / 20)
             constexpr bool kCompact = FMT == kFmtF16E5;
             constexpr size_t plane = (size_t)128 * KX * 2;
             constexpr size_t blk_bytes = kCompact ? plane + (size_t)(KX / 16) * 2048 : 2 * plane;
@@ -1449,8 +1469,20 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 for (int c = 0; c < 2; ++c) {
                     if (c == 1 && gs >= total1) break;
                     const uint8_t* xb = xbase + blk_of(c, gs) * blk_bytes;
+                    if (kCompact && !(kExp & 1) && CF_L2_PREFETCH) {
+                        // The ring holds about one entry, so an entry's chunks are requested only while the entry
+                        // before it is being consumed, and when two x parts run back to back the second one waited
+                        // an HBM latency (~1 500 cycles) per chunk.  Ask L2 for the NEXT entry one entry ahead.
+                        const int nc = (c == 0 && gs < total1) ? 1 : 0, ngs = nc ? gs : gs + 1;
+                        if (ngs < total0 && (nc == 0 || ngs < total1)) {
+                            const uint8_t* nb = xbase + blk_of(nc, ngs) * blk_bytes;
+                            bulk_prefetch_l2(nb, (uint32_t)plane);
+                            bulk_prefetch_l2(nb + plane, (uint32_t)(KX / 16) * 2048);
+                        }
+                    }
                     for (int kk = 0; kk < Cfg::kChunks; ++kk) {
                         mbar_wait(&bars[Cfg::kBarEmpty + st], par);
+                        CF_TRC(5, gs, 80 + kk);
                         uint8_t* dst = smem + Cfg::kRing + st * 8192;
                         uint64_t* landed = &bars[(kCompact ? Cfg::kBarTma : Cfg::kBarFull) + st];
                         if (kExp & 1) { mbar_arrive(landed); if (++st == Cfg::kStages) { st = 0; par ^= 1; } continue; }
@@ -1468,14 +1500,19 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 }
             }
         }
-    } else if (warp == 19) {
+    } else if (warp >= 19) {
         // ------------------------------------------------------------ hi-byte slab of every landed chunk (f16e5 input)
-        if (FMT == kFmtF16E5) {
+        // kGruF2Converters warps, warp 19 + i taking the ring stages == i (mod kGruF2Converters): a chunk's
+        // conversion is a serial ~30-instruction chain on a sub-partition it shares with four epilogue warps, and
+        // with one warp that chain paced the whole x part.
+        if (FMT == kFmtF16E5 && warp < 19 + kGruF2Converters) {
+            static_assert(Cfg::kStages % kGruF2Converters == 0, "converter warps split the ring by stage");
             const int total0 = tiles_of(0) * kWindow, total1 = tiles_of(1) * kWindow;
             const int n_chunks = (total0 + total1) * Cfg::kChunks;
-            uint32_t st = 0, par = 0;
-            for (int cn = 0; cn < n_chunks; ++cn) {
+            uint32_t st = warp - 19, par = 0;
+            for (int cn = warp - 19; cn < n_chunks; cn += kGruF2Converters) {
                 mbar_wait(&bars[Cfg::kBarTma + st], par);
+                if (lane == 0 && warp == 19) CF_TRC(4, cn / (2 * Cfg::kChunks), 70);
                 uint8_t* stage = smem + Cfg::kRing + st * 8192;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -1488,7 +1525,8 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[Cfg::kBarFull + st]);
-                if (++st == Cfg::kStages) { st = 0; par ^= 1; }
+                if (lane == 0 && warp == 19) CF_TRC(4, cn / (2 * Cfg::kChunks), 71);
+                if ((st += kGruF2Converters) >= Cfg::kStages) { st -= Cfg::kStages; par ^= 1; }
             }
         }
     } else if (warp >= 16 && warp < 18) {
@@ -1523,50 +1561,82 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 // x part: needs the previous step's accumulators drained
                 if (gs > 0) mbar_wait(&b[Cfg::kBarCfree], (gs - 1) & 1);
                 if (lane == 0) CF_TR(c, gs, 10);
-                for (int kk = 0; kk < Cfg::kChunks; ++kk, ++cn) {
-                    const uint32_t st = cn % Cfg::kStages;
-                    mbar_wait(&bars[Cfg::kBarFull + st], (cn / Cfg::kStages) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t a0 = s0 + Cfg::kRing + st * 8192;
-                    if (kE5) {
-                        const uint32_t wx = s0 + Cfg::kWx + kk * 2 * (kNX * 16);
-                        umma_bf16_pred(dg, make_smem_desc(a0, 2048, 128), make_smem_desc(wx, kNX * 16, 128), idesc_x, kk != 0, elected);
-                        if (!(kExp & 2))
-                        umma_f8_pred(dg, make_smem_desc(a0 + 4096u, 2048, 128),
-                                     make_smem_desc(wx + (uint32_t)KX * kNX * 2, kNX * 16, 128), idesc_x8, 1, elected);
-                    } else {
+                // The ring stage of a chunk is a compile-time constant in the issue loop, so that the operand
+                // descriptors are `base + immediate` on the uniform datapath.  With a runtime stage they took a /10,
+                // five dependent ALU ops and predicated R2URs per MMA (~165 cycles per MMA, the x part was issue-bound:
+                // 2 650 cycles for 1 536 of tensor time).  128-wide input: an entry is one turn of the 8-stage ring
+                // (chunk kk in stage kk); 32-wide input: an entry's two chunks start at an even stage of the 10.
+                auto issue_x = [&](auto st0c) {
+                    constexpr int kSt0 = decltype(st0c)::value;
+                    static_assert(kSt0 + Cfg::kChunks <= Cfg::kStages || kNoX, "an entry does not wrap around the ring");
+                    uint32_t ring_lo = (uint32_t)make_smem_desc(s0 + Cfg::kRing, 2048, 128);
+                    uint32_t wx_lo = (uint32_t)make_smem_desc(s0 + Cfg::kWx, kNX * 16, 128);
+                    asm volatile("" : "+r"(ring_lo), "+r"(wx_lo));       // per step, not hoisted: dozens of live descriptors spill
+                    constexpr uint64_t ahi = make_smem_desc(0, 2048, 128) & 0xffffffff00000000ull;
+                    constexpr uint64_t bhi = make_smem_desc(0, kNX * 16, 128) & 0xffffffff00000000ull;
+                    const uint32_t xpar = (cn / Cfg::kStages) & 1;
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint64_t ad = make_smem_desc(a0 + (pass == 1 ? 4096u : 0u), 2048, 128);
-                            const uint32_t wx = s0 + Cfg::kWx + (pass == 2 ? (uint32_t)KX * kNX * 2 : 0u) + kk * 2 * (kNX * 16);
-                            umma_bf16_pred(dg, ad, make_smem_desc(wx, kNX * 16, 128), idesc_x, (kk | pass) != 0, elected);
+                    for (int kk = 0; kk < Cfg::kChunks; ++kk) {
+                        const int st = kSt0 + kk;
+                        mbar_wait(&bars[Cfg::kBarFull + st], xpar);
+                        if (lane == 0) CF_TRC(c, gs, 60 + kk);
+                        tc_fence_after_sync();
+                        const uint32_t a_lo = ring_lo + st * (8192 >> 4), w_lo = wx_lo + kk * (2 * kNX * 16 >> 4);
+                        if (kE5) {
+                            umma_bf16_pred(dg, ahi | a_lo, bhi | w_lo, idesc_x, kk != 0, elected);
+                            if (!(kExp & 2))
+                            umma_f8_pred(dg, ahi | (a_lo + (4096 >> 4)), bhi | (w_lo + (KX * kNX * 2 >> 4)), idesc_x8, 1, elected);
+                        } else {
+#pragma unroll
+                            for (int pass = 0; pass < 3; ++pass)
+                                umma_bf16_pred(dg, ahi | (a_lo + (pass == 1 ? 4096 >> 4 : 0)),
+                                               bhi | (w_lo + (pass == 2 ? KX * kNX * 2 >> 4 : 0)), idesc_x, (kk | pass) != 0, elected);
                         }
+                        umma_commit_pred(&bars[Cfg::kBarEmpty + st], elected);
+                        if (lane == 0) CF_TRC(c, gs, 20 + kk);
+                        if (kk == Cfg::kChunks - 1 && lane == 0) CF_TR(c, gs, 27);
                     }
-                    umma_commit_pred(&bars[Cfg::kBarEmpty + st], elected);
-                    if (kk == Cfg::kChunks - 1 && lane == 0) CF_TR(c, gs, 27);
+                };
+                if constexpr (kNoX) {
+                } else if constexpr (Cfg::kChunks == Cfg::kStages) {
+                    issue_x(std::integral_constant<int, 0>{});
+                } else {
+                    static_assert(Cfg::kStages == 10 && Cfg::kChunks == 2, "entries start at the even stages 0..8");
+                    switch (cn % Cfg::kStages) {
+                        case 0: issue_x(std::integral_constant<int, 0>{}); break;
+                        case 2: issue_x(std::integral_constant<int, 2>{}); break;
+                        case 4: issue_x(std::integral_constant<int, 4>{}); break;
+                        case 6: issue_x(std::integral_constant<int, 6>{}); break;
+                        default: issue_x(std::integral_constant<int, 8>{}); break;
+                    }
                 }
                 if (!kNoX && lane == 0) mbar_arrive(&b[Cfg::kBarXdone]);
-                // state part of the gates
+                // state part of the gates (weight descriptors = per-step base + immediate, as in the x part: kept
+                // loop-invariant, the 36 descriptors of the split-bf16 form do not fit the service warps' registers)
+                uint32_t wgh_lo = (uint32_t)make_smem_desc(s0 + Cfg::kWgh, 128 * 16, 128);
+                uint32_t wch_lo = (uint32_t)make_smem_desc(s0 + Cfg::kWch, 64 * 16, 128);
+                asm volatile("" : "+r"(wgh_lo), "+r"(wch_lo));
+                constexpr uint64_t ghi = make_smem_desc(0, 128 * 16, 128) & 0xffffffff00000000ull;
+                constexpr uint64_t chi = make_smem_desc(0, 64 * 16, 128) & 0xffffffff00000000ull;
                 mbar_wait(&b[Cfg::kBarH], par);
                 if (lane == 0) CF_TR(c, gs, 30);
                 tc_fence_after_sync();
                 if (kE5) {
 #pragma unroll
                     for (int kk = 0; kk < kH / 16; ++kk) {
-                        const uint32_t wp = s0 + Cfg::kWgh + kk * 2 * (128 * 16);
-                        umma_bf16_ts_pred(dg, ta + kk * 8, make_smem_desc(wp, 128 * 16, 128), idesc_g, !kNoX || kk != 0, elected);
+                        const uint32_t w_lo = wgh_lo + kk * (2 * 128 * 16 >> 4);
+                        umma_bf16_ts_pred(dg, ta + kk * 8, ghi | w_lo, idesc_g, !kNoX || kk != 0, elected);
                         if (!(kExp & 2))
-                        umma_f8_ts_pred(dg, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 128 * 2, 128 * 16, 128), idesc_g8, 1, elected);
+                        umma_f8_ts_pred(dg, ta + 32 + kk * 8, ghi | (w_lo + (kH * 128 * 2 >> 4)), idesc_g8, 1, elected);
                     }
                 } else {
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
-                        const uint32_t wp = s0 + Cfg::kWgh + (pass == 2 ? (uint32_t)kH * 128 * 2 : 0u);
 #pragma unroll
                         for (int kk = 0; kk < kH / 16; ++kk)
-                            umma_bf16_ts_pred(dg, ap + kk * 8, make_smem_desc(wp + kk * 2 * (128 * 16), 128 * 16, 128), idesc_g,
-                                              !kNoX || (pass | kk) != 0, elected);
+                            umma_bf16_ts_pred(dg, ap + kk * 8, ghi | (wgh_lo + (pass == 2 ? kH * 128 * 2 >> 4 : 0) + kk * (2 * 128 * 16 >> 4)),
+                                              idesc_g, !kNoX || (pass | kk) != 0, elected);
                     }
                 }
                 umma_commit_pred(&b[Cfg::kBarG], elected);
@@ -1578,27 +1648,28 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 if (kE5) {
 #pragma unroll
                     for (int kk = 0; kk < kH / 16; ++kk) {
-                        const uint32_t wp = s0 + Cfg::kWch + kk * 2 * (64 * 16);
-                        umma_bf16_ts_pred(dc, ta + kk * 8, make_smem_desc(wp, 64 * 16, 128), idesc_c, !kNoX || kk != 0, elected);
+                        const uint32_t w_lo = wch_lo + kk * (2 * 64 * 16 >> 4);
+                        umma_bf16_ts_pred(dc, ta + kk * 8, chi | w_lo, idesc_c, !kNoX || kk != 0, elected);
                         if (!(kExp & 2))
-                        umma_f8_ts_pred(dc, ta + 32 + kk * 8, make_smem_desc(wp + (uint32_t)kH * 64 * 2, 64 * 16, 128), idesc_c8, 1, elected);
+                        umma_f8_ts_pred(dc, ta + 32 + kk * 8, chi | (w_lo + (kH * 64 * 2 >> 4)), idesc_c8, 1, elected);
                     }
                 } else {
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint32_t ap = ta + (pass == 1 ? 32u : 0u);
-                        const uint32_t wp = s0 + Cfg::kWch + (pass == 2 ? (uint32_t)kH * 64 * 2 : 0u);
 #pragma unroll
                         for (int kk = 0; kk < kH / 16; ++kk)
-                            umma_bf16_ts_pred(dc, ap + kk * 8, make_smem_desc(wp + kk * 2 * (64 * 16), 64 * 16, 128), idesc_c,
-                                              !kNoX || (pass | kk) != 0, elected);
+                            umma_bf16_ts_pred(dc, ap + kk * 8, chi | (wch_lo + (pass == 2 ? kH * 64 * 2 >> 4 : 0) + kk * (2 * 64 * 16 >> 4)),
+                                              idesc_c, !kNoX || (pass | kk) != 0, elected);
                     }
                 }
                 umma_commit_pred(&b[Cfg::kBarC], elected);
                 if (lane == 0) CF_TR(c, gs, 41);
             }
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kGruF2EpiRegs));
         // ------------------------------------------------------------ epilogue: 16 warps serve BOTH chains
         // Thread = (window row, 16 of the 64 hidden units) of both chains.  A chain's step has two epilogue phases,
         // R (reset gate -> r*h operand) after its gate MMAs and C (update gate, candidate, new state) after its
@@ -1614,10 +1685,20 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
         const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
         const int tot[2] = {tiles_of(0) * kWindow, tiles_of(1) * kWindow};
         float2 h2[2][8];                       // state of this thread's 16 units, per chain, as packed pairs
-        // position of each chain inside its tile and the tile's first block, advanced step by step (no division)
+        // position of each chain inside its tile and the block (tile * 35 + time step) it is at, advanced step by
+        // step: no division, no 64-bit index arithmetic; the thread-constant parts of every address are folded
+        // into base pointers once
         int spos[2] = {0, 0};
-        size_t tile_blk[2] = {(size_t)(slot * 2) * kWindow, (size_t)(slot * 2 + 1) * kWindow};
-        auto cur_blk = [&](int c) -> size_t { return tile_blk[c] + (dir ? kWindow - 1 - spos[c] : spos[c]); };
+        const uint32_t blk_step = dir ? 0xffffffffu : 1u;                                  // +-1 per step
+        const uint32_t blk_jump = (uint32_t)stride * kWindow - blk_step * (kWindow - 1);    // last block -> next tile's first
+        uint32_t cblk[2] = {(uint32_t)(slot * 2) * kWindow + (dir ? kWindow - 1 : 0),
+                            (uint32_t)(slot * 2 + 1) * kWindow + (dir ? kWindow - 1 : 0)};
+        uint8_t* const y_main = reinterpret_cast<uint8_t*>(y_out) + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 16;
+        const int32_t y_lo_delta = FMT_OUT == kFmtF16E5
+            ? 128 * 2 * kH * 2 + ((dir * kH + j0) / 16 * 128 + row) * 16 - ((dir * kH + j0) / 8 * 128 + row) * 16
+            : 128 * 2 * kH * 2;
+        float* const head_base = head_part + (dir * 4 + us) * 128 + row;
+        const float* const xs_base = x_scalar + row;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1674,7 +1755,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             uint64_t* b = &bars[8 * c];
             const uint32_t t_acc = t_row + c * 256 + j0;
             const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
-            const float xv = kNoX ? __ldg(x_scalar + cur_blk(c) * 128 + row) : 0.f;
+            const float xv = kNoX ? __ldg(xs_base + (size_t)cblk[c] * 128) : 0.f;
             if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 49);
             mbar_wait(&b[Cfg::kBarG], gs & 1);
             if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 50);
@@ -1703,9 +1784,9 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
             uint64_t* b = &bars[8 * c];
             const uint32_t t_acc = t_row + c * 256 + j0;
             const uint32_t t_ahi = t_row + c * 256 + 3 * kH + j0 / 2, t_alo = t_ahi + 32;
-            const size_t blk = cur_blk(c);
+            const uint32_t blk = cblk[c];
             const int s = spos[c];
-            const float xv = kNoX ? __ldg(x_scalar + blk * 128 + row) : 0.f;
+            const float xv = kNoX ? __ldg(xs_base + (size_t)blk * 128) : 0.f;
             float2 u2[8];
             {
                 uint32_t au[16];
@@ -1754,32 +1835,28 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
                 }
                 // hi[] = main words of the 16 values; lo[] = 4 words of remainder bytes then 4 of hi bytes (f16e5) /
                 // 8 words of bf16 remainders (split bf16)
-                uint8_t* yb = reinterpret_cast<uint8_t*>(y_out) + blk * gru_out_block_bytes(FMT_OUT);
-                uint8_t* ym = yb + ((size_t)(dir * kH + j0) / 8 * 128 + row) * 16;
+                uint8_t* ym = y_main + (size_t)blk * gru_out_block_bytes(FMT_OUT);
                 *reinterpret_cast<uint4*>(ym) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(ym + 2048) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                if (FMT_OUT == kFmtF16E5) {
-                    // compact form: only the remainder bytes travel (one 2 KB slab per K = 16 chunk of the block)
-                    *reinterpret_cast<uint4*>(yb + 128 * 2 * kH * 2 + ((size_t)(dir * kH + j0) / 16 * 128 + row) * 16) =
-                        make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                } else {
-                    *reinterpret_cast<uint4*>(ym + 128 * 2 * kH * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(ym + 128 * 2 * kH * 2 + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                }
+                // compact form: only the remainder bytes travel (one 2 KB slab per K = 16 chunk of the block)
+                *reinterpret_cast<uint4*>(ym + y_lo_delta) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                if (FMT_OUT != kFmtF16E5)
+                    *reinterpret_cast<uint4*>(ym + y_lo_delta + 2048) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
             if (head_part) {
                 const float* hw = head_w + dir * kH + j0;
                 float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc2 = ffma2(h2[c][i], __ldg(reinterpret_cast<const float2*>(hw) + i), acc2);
-                head_part[((blk * 2 + dir) * 4 + us) * 128 + row] = acc2.x + acc2.y;
+                head_base[(size_t)blk * 1024] = acc2.x + acc2.y;
             }
             if (s + 1 == kWindow) {
                 spos[c] = 0;
-                tile_blk[c] += (size_t)stride * kWindow;
+                cblk[c] = blk + blk_jump;
                 if (more) begin_tile(c);                 // the chain's next tile starts from a zero state
             } else {
                 spos[c] = s + 1;
+                cblk[c] = blk + blk_step;
             }
             if (warp == 0 && lane == 0) CF_TR(2 + c, gs, 56);
         };
@@ -1800,6 +1877,7 @@ tc_gru_fused2_kernel(const uint8_t* __restrict__ wpk, const float* __restrict__ 
 }
 
 #undef CF_TR
+#undef CF_TRC
 
 // ====================================================================== TK5: head
 // p = sigmoid(sum of the partial dots + b), scattered to sample order with the padding cut
@@ -1999,8 +2077,8 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 ProfScope ps(prof, KC_K4_GRU, stream);
                 long long* trace_dev = nullptr;
                 if (e->trace_path && !e->trace_done && L.in != kC) {
-                    CF_CUDA(cudaMalloc(&trace_dev, 5 * 200 * 2 * sizeof(long long)));
-                    CF_CUDA(cudaMemsetAsync(trace_dev, 0, 5 * 200 * 2 * sizeof(long long), stream));
+                    CF_CUDA(cudaMalloc(&trace_dev, 6 * 200 * 2 * sizeof(long long)));
+                    CF_CUDA(cudaMemsetAsync(trace_dev, 0, 6 * 200 * 2 * sizeof(long long), stream));
                 }
                 const int grid2 = 2 * (int)std::min<int64_t>((tiles + 1) / 2, e->n_sms / 2);
                 const float* hw_l = last ? e->head_w : nullptr;
@@ -2033,10 +2111,10 @@ int tc_forward(TcEngine* e, const HostModel& hm, const int16_t* raw, const doubl
                 if (trace_dev) {
                     // debug (CF_TC_TRACE=<file>): dump the timeline of block 0 once; results are unaffected
                     CF_CUDA(cudaStreamSynchronize(stream));
-                    std::vector<long long> host(5 * 200 * 2);
+                    std::vector<long long> host(6 * 200 * 2);
                     CF_CUDA(cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
                     if (FILE* f = fopen(e->trace_path, "w")) {
-                        for (int rg = 0; rg < 5; ++rg)
+                        for (int rg = 0; rg < 6; ++rg)
                             for (int k = 0; k < 200; ++k)
                                 if (host[(rg * 200 + k) * 2 + 1])
                                     fprintf(f, "%d %lld %lld\n", rg, host[(rg * 200 + k) * 2], host[(rg * 200 + k) * 2 + 1]);

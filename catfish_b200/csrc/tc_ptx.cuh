@@ -107,7 +107,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {           // the 
 
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (see header comment).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__host__ __device__ constexpr uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
