@@ -33,3 +33,4 @@ timeout 600 python tools/tail_accuracy.py 12 256 > gpurun_out/${R}_tail_accuracy
 timeout 300 python tools/latency_long_reads.py 1 8 64 > gpurun_out/${R}_long_reads.txt 2>&1; tail -3 gpurun_out/${R}_long_reads.txt
 timeout 600 python tools/soak.py > gpurun_out/${R}_soak.txt 2>&1; tail -2 gpurun_out/${R}_soak.txt
 tools/mma_rate.bin > gpurun_out/${R}_mma_rate.txt 2>&1
+nvidia-smi -q -d POWER,CLOCK > gpurun_out/${R}_nvidia_smi_power.txt 2>&1
