@@ -200,6 +200,7 @@ def infer_reads_arrays(raws, model, threshold=0.5, min_run=15, extension_left=11
 
 _PIPELINE_MIN_SAMPLES = 24_000_000      # batches of at least ~2 engine passes take the pipelined path
 _GROUP_SAMPLES = 10_400_000             # one engine pass (2368 tiles of 128 windows) per group
+_FIRST_GROUP_SAMPLES = int(os.environ.get("CF_FIRST_GROUP_SAMPLES", 2_600_000))
 _DEVBUF = {}                            # device index -> dict of cached device / pinned result buffers
 
 
@@ -218,7 +219,9 @@ def _infer_reads_pipelined(arrays, offsets, model, threshold, min_run, ext_left,
     cuts = [0]
     while cuts[-1] < n_reads:
         lo = cuts[-1]
-        hi = int(np.searchsorted(offsets, offsets[lo] + _GROUP_SAMPLES, side="right")) - 1
+        # the first group is a quarter pass: the GPU starts after ~0.5 ms of staging instead of ~2 ms
+        want = _GROUP_SAMPLES if lo else _FIRST_GROUP_SAMPLES
+        hi = int(np.searchsorted(offsets, offsets[lo] + want, side="right")) - 1
         cuts.append(min(n_reads, max(hi, lo + 1)))
     groups = list(zip(cuts[:-1], cuts[1:]))
     caps = [int(lib.cf_max_intervals(int(offsets[hi] - offsets[lo]), hi - lo, min_run)) for lo, hi in groups]
