@@ -610,7 +610,7 @@ def configs_leg(args, resnetrnn, peaks):
     steps = 3
     out = {}
 
-    def measure(model, kind, step_fn, samples_per_step, reads_per_step, describe):
+    def measure(model, kind, step_fn, samples_per_step, reads_per_step, describe, flops_of=None):
         handle = model.handle
         for i in range(3):
             step_fn(i)
@@ -626,7 +626,7 @@ def configs_leg(args, resnetrnn, peaks):
         prof = _cabi.profile_read(handle)
         _cabi.profile_enable(handle, False)
         fused = prof.get("k3_gru_input_proj", (0.0, 0))[0] == 0.0
-        flops = flops_per_sample(kind, fused)
+        flops = flops_of(fused) if flops_of else flops_per_sample(kind, fused)
         total = samples_per_step * steps
         roof = dominant_roofline(prof, ms, total, flops, peaks)
         ent = {"workload": describe, "samples_per_sec": total / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
@@ -685,6 +685,31 @@ def configs_leg(args, resnetrnn, peaks):
                                           "configs[1]: RNN-only (layer_size 64 x 3 layers, seeded random-init), 4 000 "
                                           "synthetic reads x 20 000 samples per step")
     del rawr_dev, keep, rnn
+    torch.cuda.empty_cache()
+    # configs[1], stress variant of SURVEY 8d (networks/train_validate.py:330): RNN-only H = 256 x 5 layers.  Its 384 KB
+    # of recurrent weights per direction do not fit one SM, so it runs on the fp32 CUDA-core engine (DESIGN.md
+    # section 9); the fraction is still quoted against the bf16 tensor peak.
+    hp256 = dict(hp, layer_size=256, n_layers=5)
+    rnn256 = neural_network.build_model("RNN", engine=args.engine, **hp256)
+    rnn256.set_weights(W.random_init("RNN", seed=13, layer_size=256, n_layers=5))
+    raws, offs = synth.concat_reads(synth.synth_reads([20000] * 32, base_seed=5200))
+    raws_dev = torch.from_numpy(raws).cuda()
+    fn, keep = reads_step(rnn256, raws_dev, offs, 32)
+
+    def flops256(fused):
+        xproj = 2.0 * 2 * 1 * 768 + 4 * (2.0 * 2 * 512 * 768)
+        rec = 5 * (2.0 * 2 * 256 * 768)
+        d = {"k5_head": 1024.0}
+        if fused:
+            d["k4_gru_recurrence"] = xproj + rec
+        else:
+            d["k3_gru_input_proj"], d["k4_gru_recurrence"] = xproj, rec
+        return d
+    out["c1_rnn_only_h256x5_stress"] = measure(rnn256, "RNN", fn, int(offs[-1]), 32,
+                                               "configs[1] stress variant: RNN-only layer_size 256 x 5 layers (10.2 MFLOP "
+                                               "per sample), seeded random-init, 32 synthetic reads x 20 000 samples per step",
+                                               flops_of=flops256)
+    del raws_dev, keep, rnn256
     torch.cuda.empty_cache()
     # configs[2]: ResNet-only (resnet_class.py:23), random-init, 1 048 576 windows per call through cf_infer_windows
     res = neural_network.build_model("ResNet", engine=args.engine, **hp)
