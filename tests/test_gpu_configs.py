@@ -140,3 +140,23 @@ def test_sharded_job_single_rank_equals_batch_call(shipped_weights):
     assert lens == want_l and len(hps) == len(reads)
     assert all(a == b for a, b in zip(hps, want_h))
     assert hps[5].tolist() == want_h[5].tolist() and hps[1:3][1] == want_h[2]
+    # the call leaves its host wall-clock breakdown for bench.py's job leg
+    assert set(sharding.last_timing) == {"partition_s", "infer_s", "gather_s"}
+    assert all(v >= 0 for v in sharding.last_timing.values())
+
+
+def test_reserve_gather_presizes_the_pinned_staging():
+    """sharding.reserve_gather: the NCCL gather's pinned staging is sized once for the largest shard (rank 0 also
+    gets the receive buffer for every rank) and later, smaller requests reuse it."""
+    from catfish_b200 import sharding
+    sharding._PIN.clear()
+    sharding.reserve_gather(100, 5000, rank=0, world_size=4)
+    need = 3 * 100 + 1 + 2 * 5000
+    send, recv = sharding._PIN["send"], sharding._PIN["recv"]
+    assert send.is_pinned() and send.numel() >= need and recv.numel() >= 4 * need
+    sharding.reserve_gather(10, 50, rank=0, world_size=4)
+    assert sharding._PIN["send"] is send and sharding._PIN["recv"] is recv
+    sharding._PIN.clear()
+    sharding.reserve_gather(100, 5000, rank=1, world_size=4)
+    assert "recv" not in sharding._PIN
+    sharding._PIN.clear()
