@@ -18,7 +18,8 @@
 //         x rows of gates/kernel and candidate/kernel, hoisted out of the time loop)
 //   TK4   tc_gru_kernel    GRU recurrence over the 35 steps of a window tile, both directions
 //         as two independent chains per CTA (rnn_class.py:142-175)
-// (CF_TC_UNFUSED=1, and layer 0 of RNN-only networks whose input is 1 wide).
+// (CF_TC_UNFUSED=1 only; layer 0 of RNN-only networks, whose input is 1 wide, is the KX = 1 form of TK4G:
+// no x MMAs, the rank-1 update x_t * w_row is added in the epilogue).
 //
 // Data layout: a tile is 128 windows (= 128 TMEM lanes = UMMA M); a block is (tile, t), one of
 // the 35 positions of those windows.  Activations that feed an MMA live in global memory as
