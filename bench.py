@@ -289,10 +289,13 @@ def dominant_roofline(prof, ms_total, samples, flops, peaks):
 
 
 def source_fingerprint():
-    """sha1 over the CUDA sources: ties a committed ncu traffic figure to the kernels it was captured from."""
+    """sha1 over the sources of the kernels the committed ncu traffic figures belong to (the tensor-core engine and
+    every header of csrc/): ties `profiles/r2_traffic.json` to the kernels being timed."""
     h = hashlib.sha1()
     csrc = os.path.join(ROOT, "catfish_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
+        if name != "tc_engine.cu" and not name.endswith((".cuh", ".h")):
+            continue
         with open(os.path.join(csrc, name), "rb") as f:
             h.update(name.encode())
             h.update(f.read())

@@ -359,35 +359,52 @@ __device__ __forceinline__ int64_t run_start_lb(const unsigned* __restrict__ lwo
 
 // Count (EMIT = false): qualifying run ends per block; the LAST block to finish scans the block counts into
 // block_base (so no separate scan launch).  Emit (EMIT = true): intervals in global rank order.
+// A thread owns kBitsWordsPerThread consecutive words (one 128-bit load each of the label and boundary words):
+// with one word per thread the 2e6 words of a 512-read batch were 7 waves of 256-thread blocks, each a
+// load -> look-back -> block scan latency chain (39 us per launch for 8 MB of bits).
+constexpr int kBitsThreads = 256, kBitsWordsPerThread = 4, kBitsWordsPerBlock = kBitsThreads * kBitsWordsPerThread;
 template <bool EMIT>
-__global__ void __launch_bounds__(kWordsPerBlock)
+__global__ void __launch_bounds__(kBitsThreads)
 k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restrict__ bwords, int64_t n_words,
                     const int64_t* __restrict__ offsets, int n_reads, int min_run, int ext_left, int ext_right,
                     unsigned* __restrict__ block_cnt, int64_t* __restrict__ block_base, unsigned* __restrict__ done_counter,
                     int64_t* __restrict__ run_start_global, int64_t* __restrict__ intervals, int64_t capacity) {
-    __shared__ unsigned warp_sums[kWordsPerBlock / 32];
-    __shared__ long long scan_sums[kWordsPerBlock / 32];
+    __shared__ unsigned warp_sums[kBitsThreads / 32];
+    __shared__ long long scan_sums[kBitsThreads / 32];
     __shared__ long long scan_carry;
     __shared__ int is_last;
-    const int64_t w = (int64_t)blockIdx.x * kWordsPerBlock + threadIdx.x;
-    unsigned L = 0, E = 0;
-    if (w < n_words) {
-        L = lwords[w];
-        unsigned next = 0, bnext = 0;
-        if (w + 1 < n_words) { next = lwords[w + 1] & 1u; bnext = bwords[w + 1] & 1u; }
-        E = L & (~((L >> 1) | (next << 31)) | (bwords[w] >> 1) | (bnext << 31));
+    constexpr int W = kBitsWordsPerThread;
+    const int64_t w0 = ((int64_t)blockIdx.x * kBitsThreads + threadIdx.x) * W;
+    unsigned L[W + 1], B[W + 1];                // this thread's words and the one after them (for the carry bits)
+    if (w0 + W < n_words) {                      // both arrays are 16-byte aligned and hold n_words + 1 words
+        const uint4 l4 = *reinterpret_cast<const uint4*>(lwords + w0), b4 = *reinterpret_cast<const uint4*>(bwords + w0);
+        L[0] = l4.x; L[1] = l4.y; L[2] = l4.z; L[3] = l4.w; L[W] = lwords[w0 + W];
+        B[0] = b4.x; B[1] = b4.y; B[2] = b4.z; B[3] = b4.w; B[W] = bwords[w0 + W];
+    } else {
+#pragma unroll
+        for (int j = 0; j <= W; ++j) {
+            const bool in = w0 + j < n_words;
+            L[j] = in ? lwords[w0 + j] : 0u;
+            B[j] = in ? bwords[w0 + j] : 0u;
+        }
     }
-    unsigned qual = 0;
+    unsigned qual[W];
     int64_t starts[4];
     int nq = 0;
-    for (unsigned e = E; e; e &= e - 1) {
-        const int eb = __ffs(e) - 1;
-        const int64_t s = run_start_lb(lwords, bwords, w, eb);
-        const int64_t len = (w << 5) + eb - s + 1;
-        if (len >= min_run) {
-            qual |= 1u << eb;
-            if (nq < 4) starts[nq] = s;
-            ++nq;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        // run ends: a set label bit whose successor is clear or starts another read
+        const unsigned E = L[j] & (~((L[j] >> 1) | ((L[j + 1] & 1u) << 31)) | (B[j] >> 1) | ((B[j + 1] & 1u) << 31));
+        qual[j] = 0;
+        for (unsigned e = E; e; e &= e - 1) {
+            const int eb = __ffs(e) - 1;
+            const int64_t s = run_start_lb(lwords, bwords, w0 + j, eb);
+            const int64_t len = ((w0 + j) << 5) + eb - s + 1;
+            if (len >= min_run) {
+                qual[j] |= 1u << eb;
+                if (nq < 4) starts[nq] = s;
+                ++nq;
+            }
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -400,7 +417,7 @@ k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restr
     if (lane == 31) warp_sums[warp] = inc;
     __syncthreads();
     unsigned base = 0, total = 0;
-    for (int i = 0; i < kWordsPerBlock / 32; ++i) {
+    for (int i = 0; i < kBitsThreads / 32; ++i) {
         unsigned v = warp_sums[i];
         if (i < warp) base += v;
         total += v;
@@ -416,7 +433,7 @@ k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restr
         if (!is_last) return;
         __threadfence();
         const int64_t n = gridDim.x;
-        for (int64_t b0 = 0; b0 < n; b0 += kWordsPerBlock) {
+        for (int64_t b0 = 0; b0 < n; b0 += kBitsThreads) {
             const int64_t i = b0 + threadIdx.x;
             const long long v = i < n ? (long long)__ldcg(block_cnt + i) : 0;
             long long sc = v;
@@ -428,7 +445,7 @@ k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restr
             if (lane == 31) scan_sums[warp] = sc;
             __syncthreads();
             long long wbase = 0, tot = 0;
-            for (int k = 0; k < kWordsPerBlock / 32; ++k) {
+            for (int k = 0; k < kBitsThreads / 32; ++k) {
                 const long long t = scan_sums[k];
                 if (k < warp) wbase += t;
                 tot += t;
@@ -443,15 +460,18 @@ k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restr
     } else {
         int64_t rank = block_base[blockIdx.x] + base + inc - (unsigned)nq;
         int k = 0;
-        for (unsigned q = qual; q; q &= q - 1, ++k, ++rank) {
-            const int eb = __ffs(q) - 1;
-            const int64_t s = k < 4 ? starts[k] : run_start_lb(lwords, bwords, w, eb);
-            const int64_t len = (w << 5) + eb - s + 1;
-            run_start_global[rank] = s;
-            if (rank < capacity) {
-                const int64_t local = s - offsets[find_read(offsets, n_reads, s)];
-                intervals[2 * rank] = local - ext_left;
-                intervals[2 * rank + 1] = local + len + ext_right;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            for (unsigned q = qual[j]; q; q &= q - 1, ++k, ++rank) {
+                const int eb = __ffs(q) - 1;
+                const int64_t s = k < 4 ? starts[k] : run_start_lb(lwords, bwords, w0 + j, eb);
+                const int64_t len = ((w0 + j) << 5) + eb - s + 1;
+                run_start_global[rank] = s;
+                if (rank < capacity) {
+                    const int64_t local = s - offsets[find_read(offsets, n_reads, s)];
+                    intervals[2 * rank] = local - ext_left;
+                    intervals[2 * rank + 1] = local + len + ext_right;
+                }
             }
         }
     }
@@ -459,12 +479,13 @@ k6_runs_bits_kernel(const unsigned* __restrict__ lwords, const unsigned* __restr
 
 int k6_bits_prepare(IntervalScratch& s, int64_t total_samples, LabelBits* out, cudaStream_t stream) {
     const int64_t n_words = ceil_div(total_samples > 0 ? total_samples : 1, 32);
-    CF_TRY(s.bits.ensure(sizeof(unsigned) * (size_t)(3 * (n_words + 1))));
+    const int64_t stride = (n_words + 1 + 3) / 4 * 4;             // both word arrays 16-byte aligned (128-bit loads)
+    CF_TRY(s.bits.ensure(sizeof(unsigned) * (size_t)(3 * stride)));
     CF_TRY(s.misc.ensure(256));
     static_assert(sizeof(unsigned) == 4, "");
     out->lwords = s.bits.as<unsigned>();
-    out->bwords = out->lwords + (n_words + 1);
-    CF_CUDA(cudaMemsetAsync(out->lwords, 0, sizeof(unsigned) * (size_t)(2 * (n_words + 1)), stream));
+    out->bwords = out->lwords + stride;
+    CF_CUDA(cudaMemsetAsync(out->lwords, 0, sizeof(unsigned) * (size_t)(2 * stride), stream));
     return CF_OK;
 }
 
@@ -473,7 +494,7 @@ int k6_intervals_from_bits(IntervalScratch& s, const LabelBits& bits, const int6
                            int32_t min_run, int32_t ext_left, int32_t ext_right, cudaStream_t stream) {
     const int64_t n = total_samples;
     const int64_t n_words = ceil_div(n, 32);
-    const int64_t n_blocks = ceil_div(n_words, kWordsPerBlock);
+    const int64_t n_blocks = ceil_div(n_words, kBitsWordsPerBlock);
     CF_TRY(s.block_cnt.ensure(sizeof(unsigned) * (size_t)n_blocks + sizeof(int64_t) * (size_t)(n_blocks + 1) + 16));
     int64_t* block_base = s.block_cnt.as<int64_t>();
     unsigned* block_cnt = reinterpret_cast<unsigned*>(block_base + n_blocks + 1);
@@ -485,11 +506,11 @@ int k6_intervals_from_bits(IntervalScratch& s, const LabelBits& bits, const int6
         s.misc_zeroed = true;
     }
     unsigned* done = s.misc.as<unsigned>();
-    k6_runs_bits_kernel<false><<<(unsigned)n_blocks, kWordsPerBlock, 0, stream>>>(
+    k6_runs_bits_kernel<false><<<(unsigned)n_blocks, kBitsThreads, 0, stream>>>(
         bits.lwords, bits.bwords, n_words, offsets_dev, n_reads, min_run, ext_left, ext_right, block_cnt, block_base, done,
         nullptr, nullptr, 0);
     CF_LAUNCHED();
-    k6_runs_bits_kernel<true><<<(unsigned)n_blocks, kWordsPerBlock, 0, stream>>>(
+    k6_runs_bits_kernel<true><<<(unsigned)n_blocks, kBitsThreads, 0, stream>>>(
         bits.lwords, bits.bwords, n_words, offsets_dev, n_reads, min_run, ext_left, ext_right, nullptr, block_base, nullptr,
         run_start_global, intervals, capacity);
     CF_LAUNCHED();
