@@ -199,52 +199,50 @@ int k1_read_stats(const int16_t* raw, const int64_t* offsets_dev, int32_t n_read
 }
 
 // ---------------------------------------------------------------- long reads: several CTAs per read
-// A read is cut into chunks of kChunkSamples; every chunk is one CTA.  Pass 1 reduces the value
-// range per read (atomicMin/Max), pass 2 builds a shared-memory histogram of the chunk relative to
-// the read's minimum and adds its non-empty bins to the read's global histogram, pass 3 (one CTA per
-// read) evaluates the order statistics exactly as the one-CTA kernel does.  Used when reads are long
-// or few, so that one 1M-sample read does not sit on a single SM.
+// A read is cut into chunks of kChunkSamples; every chunk is one CTA.  ONE pass over the signal: the chunk's value
+// range (atomicMin/Max into the read's) and a shared-memory histogram addressed by `value mod kSmemBins` - as long
+// as a read spans at most kSmemBins values no two of its values share a bin, so no origin has to be known before the
+// pass (the earlier version read the signal twice: range first, then bins relative to the read's minimum).  The
+// non-empty bins are added to the read's global histogram under the same addressing; pass 2 (one CTA per read)
+// unwraps it from the read's minimum and evaluates the order statistics exactly as the one-CTA kernel does.  A read
+// spanning more values is flagged there and redone by k1_stats_wide_kernel; what its chunks added is never read.
+// Used when reads are long or few, so that one 1M-sample read does not sit on a single SM.
 __global__ void __launch_bounds__(kStatsThreads)
-k1_minmax_chunks_kernel(const int16_t* __restrict__ raw, const int32_t* __restrict__ chunk_read,
-                        const int64_t* __restrict__ chunk_beg, const int32_t* __restrict__ chunk_len,
-                        int* __restrict__ gmin, int* __restrict__ gmax) {
+k1_hist_chunks_kernel(const int16_t* __restrict__ raw, const int32_t* __restrict__ chunk_read,
+                      const int64_t* __restrict__ chunk_beg, const int32_t* __restrict__ chunk_len,
+                      int* __restrict__ gmin, int* __restrict__ gmax, unsigned* __restrict__ ghist) {
+    __shared__ unsigned hist[kSmemBins];
     __shared__ int red_min[kStatsThreads / 32], red_max[kStatsThreads / 32];
+    static_assert((kSmemBins & (kSmemBins - 1)) == 0, "bins are addressed by value & (kSmemBins - 1)");
     const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
     int vmin = 32767, vmax = -32768;
-    for_each_i16(raw + chunk_beg[c], chunk_len[c], [&](int v) { vmin = min(vmin, v); vmax = max(vmax, v); });
+    for_each_i16(raw + chunk_beg[c], chunk_len[c], [&](int v) {
+        vmin = min(vmin, v);
+        vmax = max(vmax, v);
+        atomicAdd(&hist[v & (kSmemBins - 1)], 1u);
+    });
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
         vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
         vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
     }
     if ((threadIdx.x & 31) == 0) { red_min[threadIdx.x >> 5] = vmin; red_max[threadIdx.x >> 5] = vmax; }
-    __syncthreads();
+    __syncthreads();                            // also: every bin update of the chunk is in place
+    for (int w = 0; w < kStatsThreads / 32; ++w) { vmin = min(vmin, red_min[w]); vmax = max(vmax, red_max[w]); }
+    const int r = chunk_read[c];
     if (threadIdx.x == 0) {
-        for (int w = 0; w < kStatsThreads / 32; ++w) { vmin = min(vmin, red_min[w]); vmax = max(vmax, red_max[w]); }
-        const int r = chunk_read[c];
         atomicMin(&gmin[r], vmin);
         atomicMax(&gmax[r], vmax);
     }
-}
-
-__global__ void __launch_bounds__(kStatsThreads)
-k1_hist_chunks_kernel(const int16_t* __restrict__ raw, const int32_t* __restrict__ chunk_read,
-                      const int64_t* __restrict__ chunk_beg, const int32_t* __restrict__ chunk_len,
-                      const int* __restrict__ gmin, const int* __restrict__ gmax, unsigned* __restrict__ ghist) {
-    __shared__ unsigned hist[kSmemBins];
-    const int c = blockIdx.x;
-    const int r = chunk_read[c];
-    const int base = gmin[r];
-    const int nb = gmax[r] - base + 1;
-    if (nb > kSmemBins) return;                 // wide read: handled by k1_stats_wide_kernel
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    for_each_i16(raw + chunk_beg[c], chunk_len[c], [&](int v) { atomicAdd(&hist[v - base], 1u); });
-    __syncthreads();
+    const int nb = vmax - vmin + 1;
+    if (nb > kSmemBins) return;                 // the read is wide: k1_stats_wide_kernel redoes it
     unsigned* gh = ghist + (size_t)r * kSmemBins;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-        const unsigned v = hist[i];
-        if (v) atomicAdd(&gh[i], v);
+        const int bin = (vmin + i) & (kSmemBins - 1);
+        const unsigned v = hist[bin];
+        if (v) atomicAdd(&gh[bin], v);
     }
 }
 
@@ -269,7 +267,7 @@ k1_stats_from_ghist_kernel(const int64_t* __restrict__ offsets, const int* __res
         return;
     }
     const unsigned* gh = ghist + (size_t)r * kSmemBins;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = gh[i];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = gh[(base + i) & (kSmemBins - 1)];      // unwrap
     __syncthreads();
     stats_from_hist(hist, base, nb, (unsigned)n, stats + 2 * r, sel, warp_sums);
 }
@@ -295,8 +293,6 @@ int k1_read_stats_chunked(const int16_t* raw, const int64_t* offsets_dev, int32_
     k1_init_minmax_kernel<<<(unsigned)ceil_div(n_reads, 256), 256, 0, stream>>>(gmin, gmax, n_reads);
     CF_LAUNCHED();
     if (n_chunks > 0) {
-        k1_minmax_chunks_kernel<<<(unsigned)n_chunks, kStatsThreads, 0, stream>>>(raw, chunk_read, chunk_beg, chunk_len, gmin, gmax);
-        CF_LAUNCHED();
         k1_hist_chunks_kernel<<<(unsigned)n_chunks, kStatsThreads, 0, stream>>>(raw, chunk_read, chunk_beg, chunk_len, gmin, gmax, ghist);
         CF_LAUNCHED();
     }
