@@ -472,7 +472,7 @@ static int infer_reads_device(cf_model* m, const int16_t* raw_dev, const int64_t
         if (chunks) {   // allocate before the timed bracket
             CF_TRY(m->k1_chunked.ensure(k1_chunked_scratch_bytes(n_reads)));
         }
-        ProfScope ps(&m->prof, KC_K1_STATS, stream, chunks ? 5 : 2);
+        ProfScope ps(&m->prof, KC_K1_STATS, stream, chunks ? 4 : 2);
         CF_TRY(compute_read_stats(raw0, offsets_host, offsets_dev, n_reads, m->stats.as<double>(), sc, stream));
     }
     {

@@ -97,11 +97,14 @@ __device__ __forceinline__ void select2(F f, int nb, unsigned k0, unsigned k1, i
     __syncthreads();
 }
 
-// Median and MAD from a histogram `hist` of nb bins whose bin 0 holds value `base`.
+// Median and MAD from a histogram `hist` of nb bins whose bin 0 holds value `base`; WRAP: the histogram is addressed
+// by `value mod kSmemBins` instead (bin of value v = v & (kSmemBins - 1)).
+template <bool WRAP = false>
 __device__ __forceinline__ void stats_from_hist(const unsigned* hist, int base, int nb, unsigned n,
                                                 double* stats_out, int* sel, unsigned* warp_sums) {
+    auto H = [&](int i) -> unsigned { return WRAP ? hist[(base + i) & (kSmemBins - 1)] : hist[i]; };
     const unsigned k0 = (n - 1) >> 1, k1 = n >> 1;
-    select2([&](int i) { return hist[i]; }, nb, k0, k1, sel, warp_sums);
+    select2(H, nb, k0, k1, sel, warp_sums);
     const int s2 = (sel[0] + base) + (sel[1] + base);          // 2 * shift
     __syncthreads();
     // folded histogram: d2 = |2v - s2| in [0, 2*nb]
@@ -110,8 +113,8 @@ __device__ __forceinline__ void stats_from_hist(const unsigned* hist, int base, 
         const int a = ((s2 - d2) >> 1) - base;                 // arithmetic shift: value is even
         const int b = ((s2 + d2) >> 1) - base;
         unsigned c = 0;
-        if (a >= 0 && a < nb) c += hist[a];
-        if (d2 != 0 && b >= 0 && b < nb) c += hist[b];
+        if (a >= 0 && a < nb) c += H(a);
+        if (d2 != 0 && b >= 0 && b < nb) c += H(b);
         return c;
     };
     select2(folded, 2 * nb + 1, k0, k1, sel + 2, warp_sums);
@@ -138,9 +141,16 @@ k1_stats_kernel(const int16_t* __restrict__ raw, const int64_t* __restrict__ off
         return;
     }
     const int16_t* p = raw + beg;
-    // pass A: value range
+    // ONE pass: value range and a histogram addressed by value mod kSmemBins (no two values of a read that spans at
+    // most kSmemBins values share a bin, so the range is not needed before the pass)
+    for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
     int vmin = 32767, vmax = -32768;
-    for_each_i16(p, n, [&](int v) { vmin = min(vmin, v); vmax = max(vmax, v); });
+    for_each_i16(p, n, [&](int v) {
+        vmin = min(vmin, v);
+        vmax = max(vmax, v);
+        atomicAdd(&hist[v & (kSmemBins - 1)], 1u);
+    });
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
         vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
@@ -154,12 +164,7 @@ k1_stats_kernel(const int16_t* __restrict__ raw, const int64_t* __restrict__ off
         if (threadIdx.x == 0) wide_flags[r] = 1;
         return;
     }
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    // pass B: histogram (second read of the signal comes from L2)
-    for_each_i16(p, n, [&](int v) { atomicAdd(&hist[v - vmin], 1u); });
-    __syncthreads();
-    stats_from_hist(hist, vmin, nb, (unsigned)n, stats + 2 * r, sel, warp_sums);
+    stats_from_hist<true>(hist, vmin, nb, (unsigned)n, stats + 2 * r, sel, warp_sums);
 }
 
 // ---------------------------------------------------------------- wide path: global histogram
