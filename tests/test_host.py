@@ -154,3 +154,40 @@ def test_no_cpu_fallback_without_a_device():
     m = neural_network.build_model("ResNetRNN", **weights.SHIPPED_HPARAMS)
     with pytest.raises(_cabi.CatfishError):
         m.set_weights(weights.load_shipped())            # cf_model_create -> CF_ERR_NO_DEVICE
+
+
+def test_gather_csr_single_rank_views_and_lengths():
+    """gather_csr / ShardedIntervals on one rank (no process group): per-read views in read order whatever the
+    order the shard lists its reads in, lengths as a plain list, slices and iteration like a list."""
+    from catfish_b200 import sharding
+    idx = np.array([3, 0, 2, 1])                                   # read ids in shard order
+    counts = [2, 0, 1, 3]                                          # intervals of reads 3, 0, 2, 1
+    ioff = np.concatenate([[0], np.cumsum(counts)])
+    flat = np.arange(2 * sum(counts), dtype=np.int64).reshape(-1, 2)
+    hps, lens = sharding.gather_csr(idx, np.array([30, 0, 20, 10]), ioff, flat, 4, 0, 1)
+    assert lens == [0, 10, 20, 30]
+    assert [len(h) for h in hps] == [0, 3, 1, 2]
+    assert hps[3].tolist() == flat[0:2].tolist() and hps[1].tolist() == flat[3:6].tolist()
+    assert [h.tolist() for h in hps[1:3]] == [flat[3:6].tolist(), flat[2:3].tolist()]
+    assert hps == [h.tolist() for h in hps]
+
+
+def test_partition_reads_properties():
+    """Every read in exactly one shard, shards sorted, deterministic, and the greedy guarantee: the heaviest shard
+    is at most the mean load plus one longest read."""
+    from hypothesis import given, settings, strategies as st
+    from catfish_b200 import sharding
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 200_000), min_size=1, max_size=300), st.integers(1, 8))
+    def check(lengths, n):
+        parts = sharding.partition_reads(lengths, n)
+        assert len(parts) == n
+        allidx = np.concatenate(parts)
+        assert sorted(allidx.tolist()) == list(range(len(lengths)))
+        assert all((np.diff(p) > 0).all() for p in parts if len(p) > 1)
+        again = sharding.partition_reads(lengths, n)
+        assert all((a == b).all() for a, b in zip(parts, again))
+        loads = [int(np.asarray(lengths)[p].sum()) for p in parts]
+        assert max(loads) <= sum(lengths) / n + max(lengths) * (1 - 1.0 / n) + 1e-9
+    check()
